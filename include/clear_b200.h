@@ -1,0 +1,207 @@
+/*
+ * clear_b200.h — C ABI of libclear_b200.so, the B200 (sm_100a) implementation of the CLEAR
+ * unlearning-step hot path (reference: somvy/multimodal_unlearning).
+ *
+ * The reference is pure Python: its "FFI" for this path is the set of eager PyTorch calls made by
+ *   MMTrainerForgetting.compute_loss          mm/trainer.py:168-483
+ *   CustomTrainerForgetting.compute_loss      nlp/dataloader.py:144-485
+ *   logits2probs / get_batch_loss             mm/trainer_utils.py:16-21,73-81
+ *   save_gradient_ratio                       methods/salun/generate_mask.py:17-89
+ * Each entry point below names the reference call sites it replaces.  A maintainer binds this
+ * header with ctypes; multimodal_unlearning_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a CUDA device pointer unless marked "host";
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library allocates no device
+ *     memory, frees nothing of the caller's and keeps no pointer after a call returns;
+ *   - all work is enqueued on the cudaStream_t passed in (as a void*); no hidden synchronisation;
+ *   - return value: 0 success, <0 a ClearStatus argument/shape error detected before any launch,
+ *     >0 a cudaError_t.  clear_last_error() returns a thread-local message for the last failure;
+ *   - bf16 is the storage type of hidden states, weights, logits and gradients; all arithmetic
+ *     accumulates in fp32.
+ */
+#ifndef CLEAR_B200_H_
+#define CLEAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLEAR_ABI_VERSION 1
+
+typedef enum ClearStatus {
+  CLEAR_OK = 0,
+  CLEAR_ERR_NULL = -1,      /* required pointer is NULL */
+  CLEAR_ERR_SHAPE = -2,     /* size / leading-dimension constraint violated */
+  CLEAR_ERR_ALIGN = -3,     /* pointer or stride not 16-byte aligned */
+  CLEAR_ERR_KIND = -4,      /* unknown enum value */
+  CLEAR_ERR_WORKSPACE = -5, /* workspace too small */
+  CLEAR_ERR_DEVICE = -6,    /* not an sm_100 device / driver entry point missing */
+} ClearStatus;
+
+/* Loss kinds evaluated row-wise on the logits. */
+typedef enum ClearLossKind {
+  CLEAR_KIND_CE = 0,      /* -log p[y]; HF causal-LM CE (A2) and get_batch_loss (A6c)             */
+  CLEAR_KIND_KL_FWD = 1,  /* sum_v q (log q - log p): kl_div(student, teacher)   mm/trainer.py:203 */
+  CLEAR_KIND_KL_REV = 2,  /* sum_v p (log p - log q): kl_div(teacher, student)   mm/trainer.py:237 */
+  CLEAR_KIND_NPO = 3,     /* sum_v log(1 + (p/(q+1e-8))^beta)                    mm/trainer.py:348 */
+  CLEAR_KIND_ENTROPY = 4, /* sum_v p log p                                       mm/trainer.py:195 */
+} ClearLossKind;
+
+const char* clear_last_error(void);
+int clear_abi_version(void);
+/* host out-params; fails with CLEAR_ERR_DEVICE when the current device is not compute capability 10.x */
+int clear_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense bf16 contraction on tcgen05/TMEM:  D[M,N] = A[M,K] * B[N,K]^T, fp32 accumulate.
+ * Building block of the three projections of the head (forward logits, dH, dW); exported so that
+ * tests and the roofline benchmark can drive each operand layout directly.
+ *   a_major / b_major: 0 = K-major  (operand stored row-major as [M or N, K], ld = row stride)
+ *                      1 = MN-major (operand stored row-major as [K, M or N], ld = row stride)
+ *   d_f32: 0 -> D is bf16, 1 -> D is fp32;  accumulate (fp32 only): D += instead of D =
+ *   lse_part: optional float2[M][ceil(N/256)] = (row max, sum exp(x - max)) over each 256-column
+ *             tile of the bf16-rounded D (bf16 D only); NULL to skip.
+ *   cta_group: 1, 2 (CTA-pair MMA, 256x256 tiles) or 0 = library default.
+ * Constraints: all leading dimensions multiples of 8 elements, pointers 16-byte aligned; an
+ * MN-major operand needs ld >= round_up(extent, 64).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ClearGemmArgs {
+  const void* a;
+  const void* b;
+  void* d;
+  float* lse_part;
+  int64_t lda, ldb, ldd;
+  int32_t m, n, k;
+  int32_t a_major, b_major;
+  int32_t d_f32, accumulate;
+  int32_t cta_group;
+  int32_t raster_m_fast; /* 1: walk M first (default for forward), 0: walk N first, -1: auto */
+} ClearGemmArgs;
+int clear_gemm_bf16(const ClearGemmArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss head, stage 1 — projection  z = hidden * weight^T   (reference: the lm_head nn.Linear inside
+ * `model(**inputs)`, mm/trainer.py:180,184,188-189,...; teacher: :200,217,235,...).
+ *   logits: out bf16 [n_rows, logits_ld], logits_ld >= round_up(vocab, 64), multiple of 64.
+ *   lse_part: out float2 [n_rows][clear_head_vtiles(vocab)] partial log-sum-exp statistics.
+ * ------------------------------------------------------------------------------------------- */
+int clear_head_vtiles(int vocab);
+typedef struct ClearProjectArgs {
+  const void* hidden; /* bf16 [n_rows, hidden_dim], row stride hidden_ld */
+  const void* weight; /* bf16 [vocab, hidden_dim], row stride weight_ld */
+  void* logits;
+  float* lse_part;
+  int64_t hidden_ld, weight_ld, logits_ld;
+  int64_t n_rows;
+  int32_t hidden_dim, vocab;
+  int32_t cta_group;
+} ClearProjectArgs;
+int clear_head_project(const ClearProjectArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss head, stage 2 — row-wise loss and d(loss)/d(logits), written in place over the logits.
+ * Replaces logits2probs + kl_div / CE / NPO / entropy arithmetic (mm/trainer_utils.py:16-21,
+ * mm/trainer.py:195-208,237-255,348-353; HF ForCausalLMLoss) and their autograd backward.
+ *   labels (CE only): already shifted (labels[b,t+1] at row b*T+t), -100 = ignored row.
+ *   loss_rows[i] = unscaled loss term of row i (0 for ignored CE rows).
+ *   dlogits[i,v] = grad_scale * (scale_dev ? *scale_dev : 1) * (row_weight ? row_weight[i] : 1) * dterm(i,v)
+ *   (dterm per App. A of SURVEY.md; NPO dterm = s - p*sum(s), i.e. WITHOUT the 2/(N V) factor).
+ *   Padding columns [vocab, logits_ld) are zeroed.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ClearRowLossArgs {
+  void* logits;             /* in: bf16 logits; out: bf16 dlogits */
+  const float* lse_part;    /* from clear_head_project on the same rows */
+  const void* ref_logits;   /* teacher logits bf16 (KL_FWD, KL_REV, NPO) else NULL */
+  const float* ref_lse_part;
+  const int64_t* labels;    /* CE only */
+  const float* row_weight;  /* optional [n_rows] */
+  const float* scale_dev;   /* optional device scalar */
+  float* loss_rows;         /* out [n_rows] */
+  int64_t logits_ld, ref_ld;
+  int64_t n_rows;
+  int32_t vocab;
+  int32_t kind;             /* ClearLossKind */
+  float grad_scale;
+  float beta;               /* NPO exponent (loss_beta) */
+  int32_t write_grad;       /* 0: forward only (logits left untouched) */
+} ClearRowLossArgs;
+int clear_head_rowloss(const ClearRowLossArgs* args, void* stream);
+
+/* inv_count[0] = 1 / #{i : labels[i] != -100}   (inf when none: the reference's mean CE is NaN then) */
+int clear_head_count_valid(const int64_t* labels, int64_t n_rows, float* inv_count, void* stream);
+
+/* out[0] (+)= scale * (scale_dev ? *scale_dev : 1) * sum_i loss_rows[i]   — deterministic single-block tree */
+int clear_head_reduce_rows(const float* loss_rows, int64_t n_rows, float scale, const float* scale_dev,
+                           float* out, int accumulate, void* stream);
+/* seq_sums[b] = sum_t loss_rows[b*rows_per_seq + t]   (get_batch_loss, mm/trainer_utils.py:73-81) */
+int clear_head_reduce_sequences(const float* loss_rows, int64_t n_seqs, int64_t rows_per_seq, float* seq_sums,
+                                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss head, stage 3 — backward projections (autograd of nn.Linear, K9):
+ *   dhidden[n_rows, hidden_dim] = dlogits * weight           (bf16 out; NULL to skip)
+ *   dweight[vocab, hidden_dim]  = dlogits^T * hidden         (bf16, or fp32 with optional accumulate)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ClearBackwardArgs {
+  const void* dlogits; /* bf16 [n_rows, dlogits_ld] */
+  const void* hidden;
+  const void* weight;
+  void* dhidden;
+  void* dweight;
+  int64_t dlogits_ld, hidden_ld, weight_ld, dhidden_ld, dweight_ld;
+  int64_t n_rows;
+  int32_t hidden_dim, vocab;
+  int32_t dweight_f32, accumulate;
+  int32_t cta_group;
+} ClearBackwardArgs;
+int clear_head_backward(const ClearBackwardArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SalUn saliency mask (methods/salun/generate_mask.py:17-89) and the masked update.
+ * All tensors of a model live in flat buffers; `seg_offsets` (host, n_segs+1 int64, element units,
+ * every offset a multiple of 8) delimits the per-parameter tensors — thresholds are per tensor, as
+ * in the reference (:54-85).
+ * ------------------------------------------------------------------------------------------- */
+/* acc (bf16) += grad (bf16), rounding like torch's bf16 add (generate_mask.py:41-44) */
+int clear_saliency_accumulate(void* acc, const void* grad, int64_t n, void* stream);
+/* hist[seg][bin] += #elements of segment seg whose fp16(|acc|) bit pattern == bin; bins = 32768
+ * (patterns 0x0000..0x7FFF; |x| clears the sign).  hist: uint32 [n_segs][32768], caller-zeroed.
+ * seg_offsets_dev: device copy of the offsets.  (generate_mask.py:47-49 abs + fp16 cast) */
+int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, int32_t n_segs, int64_t n_total,
+                             uint32_t* hist, void* stream);
+/* For each segment and each of n_th thresholds: k = (int64)(th * numel) (double product truncated,
+ * as Python int()); finds tau = bit pattern of the k-th largest value and the number of ties to
+ * take.  select: int64 [n_segs][n_th][2] = (tau_bits or -1 when k == 0, ties_to_take).
+ * thresholds: host doubles. */
+int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, int32_t n_segs,
+                          const double* thresholds_host, int32_t n_th, int64_t* select, void* stream);
+/* mask[i] = 1 iff fp16(|acc[i]|) > tau, or == tau and the element is among the first `ties` such
+ * elements of its segment in flat index order (stable descending sort; SURVEY.md §8c tie contract).
+ * th_index selects which threshold's (tau, ties) to use.  tie_scratch: uint32 [n_blocks] workspace,
+ * n_blocks = clear_saliency_mask_blocks(n_total). */
+int64_t clear_saliency_mask_blocks(int64_t n_total);
+int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, int32_t n_segs, int64_t n_total,
+                        const int64_t* select, int32_t n_th, int32_t th_index, uint32_t* tie_scratch,
+                        int8_t* mask, void* stream);
+/* Masked AdamW: g' = g * mask; torch _single_tensor_adam op order, fp32 states.
+ * param, grad bf16; exp_avg, exp_avg_sq fp32; mask int8 (NULL = all ones). step >= 1. */
+typedef struct ClearAdamWArgs {
+  void* param;
+  const void* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  const int8_t* mask;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;
+} ClearAdamWArgs;
+int clear_masked_adamw(const ClearAdamWArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLEAR_B200_H_ */

@@ -1,0 +1,112 @@
+"""ctypes binding of include/clear_b200.h — the only place in the package that touches the C ABI.
+
+There is deliberately no fallback: if libclear_b200.so is missing or a call fails, a RuntimeError is
+raised.  (The CPU restatement under oracle/ is test infrastructure and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libclear_b200.so"
+
+# enum ClearLossKind
+KIND_CE, KIND_KL_FWD, KIND_KL_REV, KIND_NPO, KIND_ENTROPY = range(5)
+
+EXPORTED_SYMBOLS = (
+    "clear_last_error", "clear_abi_version", "clear_device_info", "clear_gemm_bf16", "clear_head_vtiles",
+    "clear_head_project", "clear_head_rowloss", "clear_head_count_valid", "clear_head_reduce_rows",
+    "clear_head_reduce_sequences", "clear_head_backward", "clear_saliency_accumulate",
+    "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_mask_blocks", "clear_saliency_mask",
+    "clear_masked_adamw",
+)
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("d", C.c_void_p), ("lse_part", C.c_void_p),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldd", C.c_int64),
+                ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+                ("a_major", C.c_int32), ("b_major", C.c_int32),
+                ("d_f32", C.c_int32), ("accumulate", C.c_int32),
+                ("cta_group", C.c_int32), ("raster_m_fast", C.c_int32)]
+
+
+class ProjectArgs(C.Structure):
+    _fields_ = [("hidden", C.c_void_p), ("weight", C.c_void_p), ("logits", C.c_void_p), ("lse_part", C.c_void_p),
+                ("hidden_ld", C.c_int64), ("weight_ld", C.c_int64), ("logits_ld", C.c_int64),
+                ("n_rows", C.c_int64), ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("cta_group", C.c_int32)]
+
+
+class RowLossArgs(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("lse_part", C.c_void_p), ("ref_logits", C.c_void_p),
+                ("ref_lse_part", C.c_void_p), ("labels", C.c_void_p), ("row_weight", C.c_void_p),
+                ("scale_dev", C.c_void_p), ("loss_rows", C.c_void_p),
+                ("logits_ld", C.c_int64), ("ref_ld", C.c_int64), ("n_rows", C.c_int64),
+                ("vocab", C.c_int32), ("kind", C.c_int32), ("grad_scale", C.c_float), ("beta", C.c_float),
+                ("write_grad", C.c_int32)]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [("dlogits", C.c_void_p), ("hidden", C.c_void_p), ("weight", C.c_void_p),
+                ("dhidden", C.c_void_p), ("dweight", C.c_void_p),
+                ("dlogits_ld", C.c_int64), ("hidden_ld", C.c_int64), ("weight_ld", C.c_int64),
+                ("dhidden_ld", C.c_int64), ("dweight_ld", C.c_int64), ("n_rows", C.c_int64),
+                ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("dweight_f32", C.c_int32),
+                ("accumulate", C.c_int32), ("cta_group", C.c_int32)]
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("mask", C.c_void_p), ("n", C.c_int64),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step", C.c_int32)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libclear_b200.so (built by `python -m multimodal_unlearning_b200.build`).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m multimodal_unlearning_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the CLEAR loss head.")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.clear_last_error.restype = C.c_char_p
+    lib.clear_abi_version.restype = C.c_int
+    lib.clear_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    lib.clear_gemm_bf16.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.clear_head_vtiles.argtypes = [C.c_int]
+    lib.clear_head_project.argtypes = [C.POINTER(ProjectArgs), C.c_void_p]
+    lib.clear_head_rowloss.argtypes = [C.POINTER(RowLossArgs), C.c_void_p]
+    lib.clear_head_count_valid.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.clear_head_reduce_rows.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.clear_head_reduce_sequences.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.clear_head_backward.argtypes = [C.POINTER(BackwardArgs), C.c_void_p]
+    lib.clear_saliency_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.clear_saliency_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.clear_saliency_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32,
+                                          C.c_void_p, C.c_void_p]
+    lib.clear_saliency_mask_blocks.argtypes = [C.c_int64]
+    lib.clear_saliency_mask_blocks.restype = C.c_int64
+    lib.clear_saliency_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.clear_masked_adamw.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("clear_last_error", "clear_saliency_mask_blocks"):
+            fn.restype = C.c_int
+    if lib.clear_abi_version() != 1:
+        raise RuntimeError(f"libclear_b200.so ABI version {lib.clear_abi_version()} != 1; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().clear_last_error()
+        raise RuntimeError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")

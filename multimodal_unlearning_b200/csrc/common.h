@@ -1,0 +1,41 @@
+// Host-side shared helpers: error codes / thread-local last-error string, device attributes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/clear_b200.h"
+
+namespace clear {
+
+// Records a message retrievable through clear_last_error() and returns `code` (so call sites can
+// `return fail(CLEAR_ERR_SHAPE, "...")`).
+int fail(int code, const char* fmt, ...);
+// Maps a cudaError_t to the ABI convention (positive = cudaError_t) and records its string.
+int cuda_fail(cudaError_t e, const char* what);
+
+#define CLEAR_CUDA_OK(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ::clear::cuda_fail(_e, #expr); \
+  } while (0)
+
+int device_sm_count();  // cached; <0 on error
+const char* last_error();
+
+// MMA grouping used when the caller passes cta_group = 0.
+#ifndef CLEAR_DEFAULT_CTA_GROUP
+#define CLEAR_DEFAULT_CTA_GROUP 2
+#endif
+
+// bf16 GEMM launcher used by the head entry points and by clear_gemm_bf16 (tests / roofline runs).
+struct GemmOperand {
+  const void* ptr;
+  int64_t ld;  // leading dimension in elements of the row-major storage
+  int major;   // 0: K-major  (storage [MN, K]);  1: MN-major (storage [K, MN])
+};
+int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
+                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream);
+
+}  // namespace clear

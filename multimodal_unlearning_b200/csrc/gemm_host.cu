@@ -1,0 +1,208 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding (driver entry point fetched through the
+// runtime, so libcuda is never linked), kernel-variant dispatch, persistent-grid launch.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "gemm_sm100.cuh"
+
+namespace clear {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+
+const char* last_error() { return g_err; }
+
+int device_sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  cached = n;
+  return n;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// Operand tile map.  rows_box = MN extent staged per CTA (128 or 256).
+static int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int mn_extent, int k_extent, int rows_box) {
+  auto enc = encode_fn();
+  if (!enc) return fail(CLEAR_ERR_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r;
+  if (op.major == kMajorK) {
+    cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)mn_extent};
+    cuuint64_t strides[1] = {(cuuint64_t)op.ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)rows_box};
+    cuuint32_t estr[2] = {1, 1};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // storage [K, MN] row-major; one box = 64 k-rows x 64 mn-elements (128 B rows) = one column of
+    // canonical MN-major SWIZZLE_128B atoms.
+    cuuint64_t dims[2] = {(cuuint64_t)mn_extent, (cuuint64_t)k_extent};
+    cuuint64_t strides[1] = {(cuuint64_t)op.ld * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return fail(CLEAR_ERR_SHAPE, "cuTensorMapEncodeTiled(operand, major=%d) failed: CUresult %d", op.major, (int)r);
+  return 0;
+}
+
+static int make_output_map(CUtensorMap* tm, void* d, int d_is_f32, int64_t ldd, int m, int n) {
+  auto enc = encode_fn();
+  if (!enc) return fail(CLEAR_ERR_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  const int esz = d_is_f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m};
+  cuuint64_t strides[1] = {(cuuint64_t)ldd * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, d_is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CLEAR_ERR_SHAPE, "cuTensorMapEncodeTiled(output) failed: CUresult %d", (int)r);
+  return 0;
+}
+
+template <int kCtaGroup, int kMajorA, int kMajorB, int kEpi>
+static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmParams& p,
+                          cudaStream_t stream) {
+  using S = GemmShape<kCtaGroup>;
+  auto kern = gemm_bf16_kernel<kCtaGroup, kMajorA, kMajorB, kEpi>;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    CLEAR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    configured = true;
+  }
+  const int sms = device_sm_count();
+  if (sms <= 0) return fail(CLEAR_ERR_DEVICE, "cannot query SM count");
+  const int tiles = p.m_tiles * p.n_tiles;
+  int groups = sms / kCtaGroup;
+  if (groups > tiles) groups = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * kCtaGroup));
+  cfg.blockDim = dim3(S::THREADS);
+  cfg.dynamicSmemBytes = S::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CLEAR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, p));
+  return 0;
+}
+
+int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
+                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream) {
+  if (!a.ptr || !b.ptr || !d) return fail(CLEAR_ERR_NULL, "gemm: null operand");
+  if (m <= 0 || n <= 0 || k <= 0) return fail(CLEAR_ERR_SHAPE, "gemm: non-positive dims m=%d n=%d k=%d", m, n, k);
+  if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
+  if (cta_group != 1 && cta_group != 2) return fail(CLEAR_ERR_KIND, "gemm: cta_group must be 0, 1 or 2");
+  if ((a.ld % 8) || (b.ld % 8) || (ldd % (d_is_f32 ? 4 : 8)))
+    return fail(CLEAR_ERR_ALIGN, "gemm: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld ldd=%lld)",
+                (long long)a.ld, (long long)b.ld, (long long)ldd);
+  if ((reinterpret_cast<uintptr_t>(a.ptr) | reinterpret_cast<uintptr_t>(b.ptr) | reinterpret_cast<uintptr_t>(d)) & 15)
+    return fail(CLEAR_ERR_ALIGN, "gemm: pointers must be 16-byte aligned");
+  if (a.major == kMajorMN && a.ld < m) return fail(CLEAR_ERR_SHAPE, "gemm: MN-major A needs lda >= m");
+  if (b.major == kMajorMN && b.ld < n) return fail(CLEAR_ERR_SHAPE, "gemm: MN-major B needs ldb >= n");
+  if (a.major == kMajorK && a.ld < k) return fail(CLEAR_ERR_SHAPE, "gemm: lda < k");
+  if (b.major == kMajorK && b.ld < k) return fail(CLEAR_ERR_SHAPE, "gemm: ldb < k");
+  if (ldd < n) return fail(CLEAR_ERR_SHAPE, "gemm: ldd < n");
+  if (lse_part && d_is_f32) return fail(CLEAR_ERR_KIND, "gemm: lse_part requires a bf16 output");
+  if (reduce_add && !d_is_f32) return fail(CLEAR_ERR_KIND, "gemm: accumulate requires an fp32 output");
+
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  if ((rc = make_operand_map(&tmA, a, m, k, 128))) return rc;
+  if ((rc = make_operand_map(&tmB, b, n, k, 256 / cta_group))) return rc;
+  if ((rc = make_output_map(&tmD, d, d_is_f32, ldd, m, n))) return rc;
+
+  GemmParams p;
+  p.M = m; p.N = n; p.K = k;
+  p.m_tiles = (m + 128 * cta_group - 1) / (128 * cta_group);
+  p.n_tiles = (n + 255) / 256;
+  p.raster_m_fast = raster_m_fast;
+  p.reduce_add = reduce_add;
+  p.lse_part = reinterpret_cast<float2*>(lse_part);
+
+  const int epi = d_is_f32 ? kEpiStoreF32 : (lse_part ? kEpiStoreBF16Lse : kEpiStoreBF16);
+#define CLEAR_DISPATCH(CG, MA, MB, EPI)                                                     \
+  if (cta_group == CG && a.major == MA && b.major == MB && epi == EPI)                      \
+    return launch_variant<CG, MA, MB, EPI>(tmA, tmB, tmD, p, stream);
+  CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16)
+  CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16Lse)
+  CLEAR_DISPATCH(1, kMajorK, kMajorMN, kEpiStoreBF16)
+  CLEAR_DISPATCH(1, kMajorMN, kMajorMN, kEpiStoreBF16)
+  CLEAR_DISPATCH(1, kMajorMN, kMajorMN, kEpiStoreF32)
+  CLEAR_DISPATCH(2, kMajorK, kMajorK, kEpiStoreBF16)
+  CLEAR_DISPATCH(2, kMajorK, kMajorK, kEpiStoreBF16Lse)
+  CLEAR_DISPATCH(2, kMajorK, kMajorMN, kEpiStoreBF16)
+  CLEAR_DISPATCH(2, kMajorMN, kMajorMN, kEpiStoreBF16)
+  CLEAR_DISPATCH(2, kMajorMN, kMajorMN, kEpiStoreF32)
+#undef CLEAR_DISPATCH
+  return fail(CLEAR_ERR_KIND, "gemm: operand layout combination (a_major=%d, b_major=%d, epilogue=%d) is not built",
+              a.major, b.major, epi);
+}
+
+}  // namespace clear
+
+extern "C" {
+
+const char* clear_last_error(void) { return clear::last_error(); }
+int clear_abi_version(void) { return CLEAR_ABI_VERSION; }
+
+int clear_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0, maj = 0, min = 0, sms = 0;
+  CLEAR_CUDA_OK(cudaGetDevice(&dev));
+  CLEAR_CUDA_OK(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  CLEAR_CUDA_OK(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  CLEAR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  if (maj != 10) return clear::fail(CLEAR_ERR_DEVICE, "device is sm_%d%d; this library is built for sm_100a only", maj, min);
+  return 0;
+}
+
+int clear_gemm_bf16(const ClearGemmArgs* g, void* stream) {
+  if (!g) return clear::fail(CLEAR_ERR_NULL, "clear_gemm_bf16: args is NULL");
+  clear::GemmOperand a{g->a, g->lda, g->a_major};
+  clear::GemmOperand b{g->b, g->ldb, g->b_major};
+  int raster = g->raster_m_fast;
+  if (raster < 0) raster = (int64_t)g->m <= (int64_t)g->n ? 1 : 0;
+  return clear::launch_gemm_bf16(g->cta_group, a, b, g->d, g->d_f32, g->ldd, g->m, g->n, g->k, g->lse_part,
+                                 g->accumulate, raster, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (fp32 accumulate).
+//
+//   * operands staged by TMA into 128B-swizzled shared memory, K-major or MN-major (the backward
+//     projections dH = dZ*W and dW = dZ^T*H read W / dZ / H "transposed" straight from their row-major
+//     storage — no transposed copies are ever made);
+//   * tcgen05.mma (cta_group::1: 128x256x16 per CTA; cta_group::2: 256x256x16 per CTA pair) issued by
+//     one thread, fp32 accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile
+//     i overlaps the main loop of tile i+1;
+//   * epilogue warps read TMEM with tcgen05.ld, optionally fold an online log-sum-exp over the
+//     (bf16-rounded) logits of their rows, convert, stage through swizzled smem and TMA-store
+//     (or TMA reduce-add for fp32 accumulation into an existing dW).
+//
+// This is the contraction behind reference call sites A1/K1/K9: lm_head forward
+// inside `model(**inputs)` (mm/trainer.py:180-189 etc.) and its autograd backward.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace clear {
+
+enum OperandMajor : int { kMajorK = 0, kMajorMN = 1 };
+enum EpilogueKind : int {
+  kEpiStoreBF16 = 0,     // D bf16
+  kEpiStoreBF16Lse = 1,  // D bf16 + per-(row, n-tile) (max, sum-exp) partials
+  kEpiStoreF32 = 2,      // D fp32 (store or reduce-add)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles;  // in units of (128*cta_group) x 256
+  int raster_m_fast;     // 1: consecutive tiles walk M first (A small / re-read from L2), 0: N first
+  int reduce_add;        // fp32 epilogue only: accumulate into D instead of overwriting
+  float2* lse_part;      // [M][n_tiles] when kEpiStoreBF16Lse
+};
+
+template <int kCtaGroup>
+struct GemmShape {
+  static constexpr int BM = 128;                    // D rows per CTA
+  static constexpr int BN = 256;                    // D cols per tile (UMMA N)
+  static constexpr int BK = 64;                     // 128 bytes of bf16: one swizzle span
+  static constexpr int UMMA_K = 16;
+  static constexpr int B_ROWS = BN / kCtaGroup;     // B rows (N extent) each CTA stages
+  static constexpr int A_BYTES = BM * BK * 2;       // 16 KB
+  static constexpr int B_BYTES = B_ROWS * BK * 2;   // 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (kCtaGroup == 2) ? 6 : 4;
+  static constexpr int EPI_WARP_BYTES = 2 * 4096;   // two 32-row x 128 B staging buffers per warp
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int THREADS = 256;               // warps 0..3: TMA / MMA / TMEM-alloc / idle; 4..7 epilogue
+  static constexpr int TMEM_COLS = 512;             // 2 accumulator stages x 256 fp32 columns
+};
+
+// 64-bit shared-memory matrix descriptor (sm_100 "version 1"), 128B swizzle.
+//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: atoms of 64 MN-elements x 8 k-rows (1024 B); SBO = next 8 k-rows (1024 B),
+//             LBO = next 64 MN-elements (BK * 128 B = 8192 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// 32-bit instruction descriptor for kind::f16: bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_major, int b_major) {
+  return (1u << 4)                       // D format fp32
+         | (1u << 7)                     // A format bf16
+         | (1u << 10)                    // B format bf16
+         | (uint32_t(a_major) << 15)     // 0 K-major, 1 MN-major
+         | (uint32_t(b_major) << 16)
+         | (uint32_t(n >> 3) << 17)
+         | (uint32_t(m >> 4) << 24);
+}
+
+template <int kCtaGroup, int kMajorA, int kMajorB, int kEpi>
+__global__ void __launch_bounds__(GemmShape<kCtaGroup>::THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  using S = GemmShape<kCtaGroup>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (smem_raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_raw_addr);
+
+  const uint32_t epi_addr = smem_base + S::STAGES * S::STAGE_BYTES;
+  const uint32_t bar_addr = epi_addr + S::EPI_BYTES;
+  const uint32_t full_bar = bar_addr;                        // [STAGES]
+  const uint32_t empty_bar = bar_addr + S::STAGES * 8;       // [STAGES]
+  const uint32_t tfull_bar = bar_addr + 2 * S::STAGES * 8;   // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;                // [2]
+  const uint32_t tmem_slot = tempty_bar + 16;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      ptx::mbar_init(full_bar + s * 8, 1);
+      ptx::mbar_init(empty_bar + s * 8, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar + a * 8, 1);
+      ptx::mbar_init(tempty_bar + a * 8, 4 * kCtaGroup);  // one arrive per epilogue warp of each CTA
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<kCtaGroup>(tmem_slot, S::TMEM_COLS);
+  }
+  ptx::tcgen05_fence_before();
+  if constexpr (kCtaGroup == 2) ptx::cluster_sync_all(); else __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int tile_stride = gridDim.x / kCtaGroup;
+  const int tile_first = blockIdx.x / kCtaGroup;
+  const int num_kb = (p.K + S::BK - 1) / S::BK;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ==========================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = tile_first; t < num_tiles; t += tile_stride) {
+        const int mt = p.raster_m_fast ? (t % p.m_tiles) : (t / p.n_tiles);
+        const int nt = p.raster_m_fast ? (t / p.m_tiles) : (t % p.n_tiles);
+        const int m0 = (mt * kCtaGroup + (int)cta_rank) * S::BM;
+        const int n0 = nt * S::BN + (int)cta_rank * S::B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar + stage * 8, phase ^ 1u);
+          const uint32_t fb = full_bar + stage * 8;
+          if (cta_rank == 0) ptx::mbar_arrive_expect_tx(fb, S::STAGE_BYTES * kCtaGroup);
+          const uint32_t a_dst = smem_base + stage * S::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + S::A_BYTES;
+          const int k0 = kb * S::BK;
+          // K-major: one box [rows][64 k].  MN-major: one box [64 k][64 mn] per 64-element MN chunk,
+          // chunks 8 KB apart (= the descriptor's LBO).
+          if constexpr (kMajorA == kMajorK) {
+            ptx::tma_load_2d<kCtaGroup>(a_dst, &tmA, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < S::BM / 64; ++c)
+              ptx::tma_load_2d<kCtaGroup>(a_dst + c * (S::BK * 128), &tmA, fb, m0 + c * 64, k0);
+          }
+          if constexpr (kMajorB == kMajorK) {
+            ptx::tma_load_2d<kCtaGroup>(b_dst, &tmB, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < S::B_ROWS / 64; ++c)
+              ptx::tma_load_2d<kCtaGroup>(b_dst + c * (S::BK * 128), &tmB, fb, n0 + c * 64, k0);
+          }
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ============================================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(S::BM * kCtaGroup, S::BN, kMajorA, kMajorB);
+      // K-major: +32 B per UMMA_K inside the swizzle span; MN-major: +16 k-rows * 128 B.
+      constexpr uint32_t a_adv = (kMajorA == kMajorK) ? (S::UMMA_K * 2) : (S::UMMA_K * 128);
+      constexpr uint32_t b_adv = (kMajorB == kMajorK) ? (S::UMMA_K * 2) : (S::UMMA_K * 128);
+      constexpr uint32_t a_lbo = (kMajorA == kMajorK) ? 16u : (S::BK * 128);
+      constexpr uint32_t b_lbo = (kMajorB == kMajorK) ? 16u : (S::BK * 128);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int t = tile_first; t < num_tiles; t += tile_stride) {
+        ptx::mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
+        ptx::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * S::BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar + stage * 8, phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t a_src = smem_base + stage * S::STAGE_BYTES;
+          const uint32_t b_src = a_src + S::A_BYTES;
+          const uint64_t adesc = make_smem_desc(a_src, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc(b_src, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < S::BK / S::UMMA_K; ++k) {
+            ptx::umma_f16<kCtaGroup>(d_tmem, adesc + ((k * a_adv) >> 4), bdesc + ((k * b_adv) >> 4), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit<kCtaGroup>(empty_bar + stage * 8);  // frees the smem slot once the MMAs retire
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit<kCtaGroup>(tfull_bar + acc * 8);      // accumulator complete -> epilogue
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ==============================================
+    const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may read
+    const uint32_t stg = epi_addr + q * S::EPI_WARP_BYTES;
+    const uint32_t sw = (lane & 7u);
+    uint32_t nstores = 0, acc = 0, acc_phase = 0;
+    for (int t = tile_first; t < num_tiles; t += tile_stride) {
+      const int mt = p.raster_m_fast ? (t % p.m_tiles) : (t / p.n_tiles);
+      const int nt = p.raster_m_fast ? (t / p.m_tiles) : (t % p.n_tiles);
+      const int row0 = (mt * kCtaGroup + (int)cta_rank) * S::BM + (int)q * 32;
+      const int col0 = nt * S::BN;
+      ptx::mbar_wait(tfull_bar + acc * 8, acc_phase);
+      ptx::tcgen05_fence_after();
+      const uint32_t t_base = tmem_base + ((q * 32u) << 16) + acc * S::BN;
+
+      if constexpr (kEpi == kEpiStoreF32) {
+#pragma unroll 1
+        for (int c = 0; c < S::BN / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_base + c * 32, v);
+          const uint32_t buf = stg + (nstores & 1u) * 4096u;
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+          ptx::tmem_ld_wait();
+          const uint32_t rowp = buf + lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::st_shared_v4(rowp + (((uint32_t)j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && col0 + c * 32 < p.N) {
+            if (p.reduce_add) ptx::tma_reduce_add_2d(&tmD, buf, col0 + c * 32, row0);
+            else              ptx::tma_store_2d(&tmD, buf, col0 + c * 32, row0);
+          }
+          if (lane == 0) ptx::tma_store_commit();
+          ++nstores;
+        }
+      } else {
+        constexpr float kLog2e = 1.4426950408889634f;
+        float run_max = -INFINITY, run_sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < S::BN / 64; ++c) {
+          uint32_t v0[32], v1[32];
+          ptx::tmem_ld_32x32b_x32(t_base + c * 64, v0);
+          ptx::tmem_ld_32x32b_x32(t_base + c * 64 + 32, v1);
+          const uint32_t buf = stg + (nstores & 1u) * 4096u;
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+          ptx::tmem_ld_wait();
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            __nv_bfloat162 g = __floats2bfloat162_rn(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+            pk[16 + j] = *reinterpret_cast<uint32_t*>(&g);
+          }
+          if constexpr (kEpi == kEpiStoreBF16Lse) {
+            // Online log-sum-exp over the values exactly as they are stored (bf16-rounded), so that
+            // the row pass that later reads the stored logits sees probabilities that sum to one.
+            const int cbase = col0 + c * 64;
+            float x[64];
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]));
+              x[2 * j] = (cbase + 2 * j < p.N) ? f.x : -INFINITY;
+              x[2 * j + 1] = (cbase + 2 * j + 1 < p.N) ? f.y : -INFINITY;
+              cmax = fmaxf(cmax, fmaxf(x[2 * j], x[2 * j + 1]));
+            }
+            const float new_max = fmaxf(run_max, cmax);
+            const float nm2 = new_max * kLog2e;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) s += ptx::ex2_approx(fmaf(x[j], kLog2e, -nm2));
+            run_sum = run_sum * ptx::ex2_approx(fmaf(run_max, kLog2e, -nm2)) + s;
+            run_max = new_max;
+          }
+          const uint32_t rowp = buf + lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::st_shared_v4(rowp + (((uint32_t)j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && col0 + c * 64 < p.N) ptx::tma_store_2d(&tmD, buf, col0 + c * 64, row0);
+          if (lane == 0) ptx::tma_store_commit();
+          ++nstores;
+        }
+        if constexpr (kEpi == kEpiStoreBF16Lse) {
+          const int row = row0 + (int)lane;
+          if (row < p.M) p.lse_part[(size_t)row * p.n_tiles + nt] = make_float2(run_max, run_sum);
+        }
+      }
+      // every tcgen05.ld of this accumulator stage has completed (wait::ld above): hand it back
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 2) ptx::mbar_arrive_cluster(tempty_bar + acc * 8, 0);
+        else                          ptx::mbar_arrive(tempty_bar + acc * 8);
+      }
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();
+  }
+
+  // ======================================= teardown ==============================================
+  __syncwarp();
+  ptx::tcgen05_fence_before();
+  if constexpr (kCtaGroup == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<kCtaGroup>(tmem_base, S::TMEM_COLS);
+  }
+}
+
+}  // namespace clear
