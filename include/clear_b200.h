@@ -180,13 +180,15 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
 int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, int32_t n_segs,
                           const double* thresholds_host, int32_t n_th, int64_t* select, void* stream);
 /* mask[i] = 1 iff fp16(|acc[i]|) > tau, or == tau and the element is among the first `ties` such
- * elements of its segment in flat index order (stable descending sort; SURVEY.md §8c tie contract).
- * th_index selects which threshold's (tau, ties) to use.  tie_scratch: uint32 [n_blocks] workspace,
- * n_blocks = clear_saliency_mask_blocks(n_total). */
-int64_t clear_saliency_mask_blocks(int64_t n_total);
-int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, int32_t n_segs, int64_t n_total,
-                        const int64_t* select, int32_t n_th, int32_t th_index, uint32_t* tie_scratch,
-                        int8_t* mask, void* stream);
+ * elements of its tensor in flat index order (stable descending sort; SURVEY.md §8c tie contract).
+ * th_index selects which threshold's (tau, ties) of `select` to use.
+ * Work is cut into chunks of clear_saliency_chunk_elems() elements that never straddle tensors:
+ * chunk_prefix_dev: device int64 [n_segs+1], chunk_prefix[s] = sum_{t<s} ceil(numel_t / chunk);
+ * n_chunks = chunk_prefix[n_segs]; tie_scratch: uint32 [n_chunks] workspace. */
+int64_t clear_saliency_chunk_elems(void);
+int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
+                        int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
+                        uint32_t* tie_scratch, int8_t* mask, void* stream);
 /* Masked AdamW: g' = g * mask; torch _single_tensor_adam op order, fp32 states.
  * param, grad bf16; exp_avg, exp_avg_sq fp32; mask int8 (NULL = all ones). step >= 1. */
 typedef struct ClearAdamWArgs {
@@ -196,7 +198,7 @@ typedef struct ClearAdamWArgs {
   float* exp_avg_sq;
   const int8_t* mask;
   int64_t n;
-  float lr, beta1, beta2, eps, weight_decay;
+  double lr, beta1, beta2, eps, weight_decay; /* doubles: the scalar prologue runs in double like torch's */
   int32_t step;
 } ClearAdamWArgs;
 int clear_masked_adamw(const ClearAdamWArgs* args, void* stream);

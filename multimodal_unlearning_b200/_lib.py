@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = (
     "clear_last_error", "clear_abi_version", "clear_device_info", "clear_gemm_bf16", "clear_head_vtiles",
     "clear_head_project", "clear_head_rowloss", "clear_head_count_valid", "clear_head_reduce_rows",
     "clear_head_reduce_sequences", "clear_head_backward", "clear_saliency_accumulate",
-    "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_mask_blocks", "clear_saliency_mask",
+    "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_chunk_elems", "clear_saliency_mask",
     "clear_masked_adamw",
 )
 
@@ -59,8 +59,8 @@ class BackwardArgs(C.Structure):
 class AdamWArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("mask", C.c_void_p), ("n", C.c_int64),
-                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("weight_decay", C.c_float), ("step", C.c_int32)]
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("step", C.c_int32)]
 
 
 _lib = None
@@ -91,15 +91,13 @@ def load() -> C.CDLL:
     lib.clear_saliency_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     lib.clear_saliency_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32,
                                           C.c_void_p, C.c_void_p]
-    lib.clear_saliency_mask_blocks.argtypes = [C.c_int64]
-    lib.clear_saliency_mask_blocks.restype = C.c_int64
-    lib.clear_saliency_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
-                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.clear_saliency_chunk_elems.argtypes = []
+    lib.clear_saliency_chunk_elems.restype = C.c_int64
+    lib.clear_saliency_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.clear_masked_adamw.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]
     for name in EXPORTED_SYMBOLS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("clear_last_error", "clear_saliency_mask_blocks"):
-            fn.restype = C.c_int
+        getattr(lib, name)  # AttributeError here = the .so is stale / does not match include/clear_b200.h
     if lib.clear_abi_version() != 1:
         raise RuntimeError(f"libclear_b200.so ABI version {lib.clear_abi_version()} != 1; rebuild the library")
     _lib = lib

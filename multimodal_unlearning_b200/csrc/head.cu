@@ -1,0 +1,436 @@
+// Loss head of the CLEAR unlearning step: projection / row-wise loss + dlogits / backward projections.
+//
+// Reference path: `model(**inputs)` -> lm_head -> logits2probs / kl_div / HF CE / NPO /
+// entropy -> autograd (mm/trainer.py:168-449, mm/trainer_utils.py:16-21,73-81).  The reference
+// materialises 2-6 fp32 [N,V] tensors per loss; here the only [N,V]-sized storage is ONE bf16
+// buffer per projected operand (student, and teacher when the kind needs it): the projection's
+// epilogue emits the log-sum-exp statistics, the row pass turns logits into dlogits in place, and
+// the backward projections consume that buffer.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "gemm_sm100.cuh"
+
+namespace clear {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kIgnoreIndex = -100;
+
+struct RowLossParams {
+  __nv_bfloat16* logits;
+  const float2* lse_part;
+  const __nv_bfloat16* ref_logits;
+  const float2* ref_lse_part;
+  const int64_t* labels;
+  const float* row_weight;
+  const float* scale_dev;
+  float* loss_rows;
+  int64_t ld, ref_ld;
+  int vocab, n_vtiles;
+  float grad_scale, beta;
+  int write_grad;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Every warp merges the row's per-tile (max, sum-exp) partials redundantly (a few hundred bytes from
+// L2) — cheaper than a block barrier.  Returns the row's log-sum-exp in natural-log units.
+__device__ __forceinline__ float merge_lse(const float2* part, int n) {
+  const int lane = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int i = lane; i < n; i += 32) m = fmaxf(m, part[i].x);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float2 p = part[i];
+    s += p.y * exp2f((p.x - m) * kLog2e);
+  }
+  s = warp_sum(s);
+  return m + logf(s);
+}
+
+template <int kThreads>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // protects `red` against the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < kThreads / 32) ? red[lane] : 0.f;
+  return warp_sum(t);  // every thread holds the total
+}
+
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&x)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    x[2 * j] = f.x;
+    x[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+  return raw;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CE: loss_row = lse - z[y]; dz = g (p - e_y).  Streaming, one pass.  (A2, A6c)
+// ---------------------------------------------------------------------------------------------------
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) rowloss_ce_kernel(const RowLossParams a) {
+  const int64_t row = blockIdx.x;
+  __nv_bfloat16* z = a.logits + row * a.ld;
+  const int64_t y = a.labels[row];
+  const bool valid = (y != kIgnoreIndex);
+  const float w = a.row_weight ? a.row_weight[row] : 1.f;
+  if (!a.write_grad) {
+    if (threadIdx.x < 32) {
+      float loss = 0.f;
+      if (valid) loss = (merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles) - __bfloat162float(z[y])) * w;
+      if (threadIdx.x == 0) a.loss_rows[row] = loss;
+    }
+    return;
+  }
+  const int nvec = (int)(a.ld >> 3);
+  if (!valid) {  // ignored row: dlogits = 0, nothing to read
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int v = threadIdx.x; v < nvec; v += kThreads) reinterpret_cast<uint4*>(z)[v] = zero;
+    if (threadIdx.x == 0) a.loss_rows[row] = 0.f;
+    return;
+  }
+  const float lse = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
+  const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
+  const float nl2 = -lse * kLog2e;
+  const int yv = (int)(y >> 3), yj = (int)(y & 7);
+  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+    const uint4 raw = reinterpret_cast<const uint4*>(z)[v];
+    float x[8];
+    unpack8(raw, x);
+    if (v == yv) a.loss_rows[row] = (lse - x[yj]) * w;
+    const int c0 = v << 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p = ptx::ex2_approx(fmaf(x[j], kLog2e, nl2));
+      const float d = (v == yv && j == yj) ? (p - 1.f) : p;
+      x[j] = (c0 + j < a.vocab) ? g * d : 0.f;
+    }
+    reinterpret_cast<uint4*>(z)[v] = pack8(x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward KL: loss_row = sum q (lq - lp); dz = g (p - q).  Streaming, one pass.  (A4)
+// ---------------------------------------------------------------------------------------------------
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossParams a) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  __nv_bfloat16* z = a.logits + row * a.ld;
+  const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
+  const float lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
+  const float lse_t = merge_lse(a.ref_lse_part + row * a.n_vtiles, a.n_vtiles);
+  const float w = a.row_weight ? a.row_weight[row] : 1.f;
+  const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
+  const int nvec = (int)(a.ld >> 3);
+  float acc = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+    float x[8], r[8];
+    unpack8(reinterpret_cast<const uint4*>(z)[v], x);
+    unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    const int c0 = v << 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool in = (c0 + j < a.vocab);
+      const float lp = x[j] - lse_s, lq = r[j] - lse_t;
+      const float p = ptx::ex2_approx(lp * kLog2e), q = ptx::ex2_approx(lq * kLog2e);
+      if (in) acc += q * (lq - lp);
+      x[j] = in ? g * (p - q) : 0.f;
+    }
+    if (a.write_grad) reinterpret_cast<uint4*>(z)[v] = pack8(x);
+  }
+  acc = block_sum<kThreads>(acc, red);
+  if (threadIdx.x == 0) a.loss_rows[row] = acc * w;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Two-pass kinds: a row statistic is needed before any gradient element can be formed.
+//   KL_REV : K = sum p (lp - lq);            dz = g p ((lp - lq) - K)                  (A5)
+//   NPO    : S = sum s, s = t/(1+t), t = (p/(q+1e-8))^beta; loss = sum log(1+t);
+//            dz = g (s - p S)                                                          (A6)
+//   ENTROPY: E = sum p lp;                   dz = g p (lp - E)                         (A6b)
+// The second pass re-reads the row (it was just streamed by this CTA: an L2 hit).
+// ---------------------------------------------------------------------------------------------------
+template <int kKind, bool kBetaOne>
+struct RowTerm {
+  // returns (stat contribution, loss contribution); p, aux are kept for pass 2
+  __device__ static __forceinline__ void eval(float x, float r, float lse_s, float lse_t, float beta, float& p,
+                                              float& aux, float& stat, float& loss) {
+    const float lp = x - lse_s;
+    p = ptx::ex2_approx(lp * kLog2e);
+    if constexpr (kKind == CLEAR_KIND_KL_REV) {
+      const float d = lp - (r - lse_t);
+      aux = d;
+      stat = p * d;
+      loss = stat;
+    } else if constexpr (kKind == CLEAR_KIND_ENTROPY) {
+      aux = lp;
+      stat = p * lp;  // p == 0 gives 0 (the reference's fp32 softmax would give 0 * -inf = NaN; App. B #10)
+      loss = stat;
+    } else {  // NPO
+      const float q = ptx::ex2_approx((r - lse_t) * kLog2e);
+      const float A = q + 1e-8f;
+      float t, inv1pt;
+      if constexpr (kBetaOne) {
+        const float B = p + A;
+        const float invB = ptx::rcp_approx(B);
+        aux = p * invB;                                   // s = t / (1 + t) = p / (p + q + eps)
+        loss = -ptx::lg2_approx(A * invB) * kLn2;         // log(1 + t) = -log(1 - s)
+        (void)t; (void)inv1pt;
+      } else {
+        const float ratio = p * ptx::rcp_approx(A);
+        t = ptx::ex2_approx(beta * ptx::lg2_approx(ratio));
+        const float opt = 1.f + t;
+        inv1pt = ptx::rcp_approx(opt);
+        aux = t * inv1pt;
+        loss = ptx::lg2_approx(opt) * kLn2;
+      }
+      stat = aux;
+    }
+  }
+  __device__ static __forceinline__ float grad(float p, float aux, float stat_total) {
+    if constexpr (kKind == CLEAR_KIND_NPO) return aux - p * stat_total;
+    else return p * (aux - stat_total);
+  }
+};
+
+template <int kKind, bool kBetaOne, int kThreads>
+__global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLossParams a) {
+  __shared__ float red[32];
+  constexpr bool kNeedsRef = (kKind != CLEAR_KIND_ENTROPY);
+  const int64_t row = blockIdx.x;
+  __nv_bfloat16* z = a.logits + row * a.ld;
+  const __nv_bfloat16* zr = kNeedsRef ? a.ref_logits + row * a.ref_ld : nullptr;
+  const float lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
+  const float lse_t = kNeedsRef ? merge_lse(a.ref_lse_part + row * a.n_vtiles, a.n_vtiles) : 0.f;
+  const float w = a.row_weight ? a.row_weight[row] : 1.f;
+  const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
+  const int nvec = (int)(a.ld >> 3);
+  float stat = 0.f, loss = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+    float x[8], r[8];
+    unpack8(reinterpret_cast<const uint4*>(z)[v], x);
+    if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    const int c0 = v << 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p, aux, st, ls;
+      RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, lse_s, lse_t, a.beta, p, aux, st, ls);
+      if (c0 + j < a.vocab) { stat += st; loss += ls; }
+    }
+  }
+  stat = block_sum<kThreads>(stat, red);
+  if constexpr (kKind == CLEAR_KIND_NPO) loss = block_sum<kThreads>(loss, red);
+  else loss = stat;
+  if (threadIdx.x == 0) a.loss_rows[row] = loss * w;
+  if (!a.write_grad) return;
+  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+    float x[8], r[8];
+    unpack8(reinterpret_cast<const uint4*>(z)[v], x);
+    if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    const int c0 = v << 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p, aux, st, ls;
+      RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, lse_s, lse_t, a.beta, p, aux, st, ls);
+      x[j] = (c0 + j < a.vocab) ? g * RowTerm<kKind, kBetaOne>::grad(p, aux, stat) : 0.f;
+    }
+    reinterpret_cast<uint4*>(z)[v] = pack8(x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small reductions
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) count_valid_kernel(const int64_t* labels, int64_t n, float* inv_count) {
+  __shared__ float red[32];
+  float c = 0.f;  // exact in fp32 up to 2^24 rows per call
+  for (int64_t i = threadIdx.x; i < n; i += 1024) c += (labels[i] != kIgnoreIndex) ? 1.f : 0.f;
+  c = block_sum<1024>(c, red);
+  if (threadIdx.x == 0) *inv_count = 1.f / c;
+}
+
+// Fixed-shape tree (thread-strided partials, warp shuffles, one smem stage): bitwise reproducible.
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* rows, int64_t n, float scale,
+                                                           const float* scale_dev, float* out, int accumulate) {
+  __shared__ float red[32];
+  float c = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) c += rows[i];
+  c = block_sum<1024>(c, red);
+  if (threadIdx.x == 0) {
+    const float v = c * scale * (scale_dev ? *scale_dev : 1.f);
+    *out = accumulate ? (*out + v) : v;
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_sequences_kernel(const float* rows, int64_t rows_per_seq, float* seq) {
+  __shared__ float red[32];
+  const float* r = rows + (int64_t)blockIdx.x * rows_per_seq;
+  float c = 0.f;
+  for (int64_t i = threadIdx.x; i < rows_per_seq; i += 256) c += r[i];
+  c = block_sum<256>(c, red);
+  if (threadIdx.x == 0) seq[blockIdx.x] = c;
+}
+
+}  // namespace
+}  // namespace clear
+
+using namespace clear;
+
+extern "C" {
+
+int clear_head_vtiles(int vocab) { return (vocab + 255) / 256; }
+
+int clear_head_project(const ClearProjectArgs* a, void* stream) {
+  if (!a) return fail(CLEAR_ERR_NULL, "clear_head_project: args is NULL");
+  if (!a->hidden || !a->weight || !a->logits) return fail(CLEAR_ERR_NULL, "clear_head_project: null tensor");
+  if (a->n_rows <= 0 || a->n_rows > INT32_MAX || a->hidden_dim <= 0 || a->vocab <= 0)
+    return fail(CLEAR_ERR_SHAPE, "clear_head_project: bad sizes n_rows=%lld hidden=%d vocab=%d", (long long)a->n_rows,
+                a->hidden_dim, a->vocab);
+  if (a->logits_ld % 64 || a->logits_ld < a->vocab)
+    return fail(CLEAR_ERR_SHAPE, "clear_head_project: logits_ld (%lld) must be a multiple of 64 and >= vocab",
+                (long long)a->logits_ld);
+  GemmOperand A{a->hidden, a->hidden_ld, kMajorK};
+  GemmOperand B{a->weight, a->weight_ld, kMajorK};
+  return launch_gemm_bf16(a->cta_group, A, B, a->logits, 0, a->logits_ld, (int)a->n_rows, a->vocab, a->hidden_dim,
+                          a->lse_part, 0, /*raster_m_fast=*/1, static_cast<cudaStream_t>(stream));
+}
+
+int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
+  if (!a) return fail(CLEAR_ERR_NULL, "clear_head_rowloss: args is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a->logits || !a->lse_part || !a->loss_rows) return fail(CLEAR_ERR_NULL, "clear_head_rowloss: null tensor");
+  if (a->n_rows <= 0 || a->n_rows > INT32_MAX || a->vocab <= 0)
+    return fail(CLEAR_ERR_SHAPE, "clear_head_rowloss: bad sizes");
+  if (a->logits_ld % 8 || a->logits_ld < a->vocab) return fail(CLEAR_ERR_SHAPE, "clear_head_rowloss: bad logits_ld");
+  const bool needs_ref = a->kind == CLEAR_KIND_KL_FWD || a->kind == CLEAR_KIND_KL_REV || a->kind == CLEAR_KIND_NPO;
+  if (needs_ref) {
+    if (!a->ref_logits || !a->ref_lse_part) return fail(CLEAR_ERR_NULL, "clear_head_rowloss: kind %d needs teacher logits", a->kind);
+    if (a->ref_ld < a->logits_ld || a->ref_ld % 8) return fail(CLEAR_ERR_SHAPE, "clear_head_rowloss: bad ref_ld");
+  }
+  if (a->kind == CLEAR_KIND_CE && !a->labels) return fail(CLEAR_ERR_NULL, "clear_head_rowloss: CE needs labels");
+  if (a->kind == CLEAR_KIND_NPO && !(a->beta > 0.f)) return fail(CLEAR_ERR_SHAPE, "clear_head_rowloss: NPO beta must be > 0");
+
+  RowLossParams p;
+  p.logits = static_cast<__nv_bfloat16*>(a->logits);
+  p.lse_part = reinterpret_cast<const float2*>(a->lse_part);
+  p.ref_logits = static_cast<const __nv_bfloat16*>(a->ref_logits);
+  p.ref_lse_part = reinterpret_cast<const float2*>(a->ref_lse_part);
+  p.labels = a->labels;
+  p.row_weight = a->row_weight;
+  p.scale_dev = a->scale_dev;
+  p.loss_rows = a->loss_rows;
+  p.ld = a->logits_ld;
+  p.ref_ld = a->ref_ld;
+  p.vocab = a->vocab;
+  p.n_vtiles = clear_head_vtiles(a->vocab);
+  p.grad_scale = a->grad_scale;
+  p.beta = a->beta;
+  p.write_grad = a->write_grad;
+  const unsigned grid = (unsigned)a->n_rows;
+  switch (a->kind) {
+    case CLEAR_KIND_CE:
+      rowloss_ce_kernel<256><<<grid, 256, 0, stream>>>(p);
+      break;
+    case CLEAR_KIND_KL_FWD:
+      rowloss_klfwd_kernel<256><<<grid, 256, 0, stream>>>(p);
+      break;
+    case CLEAR_KIND_KL_REV:
+      rowloss_twopass_kernel<CLEAR_KIND_KL_REV, true, 512><<<grid, 512, 0, stream>>>(p);
+      break;
+    case CLEAR_KIND_ENTROPY:
+      rowloss_twopass_kernel<CLEAR_KIND_ENTROPY, true, 512><<<grid, 512, 0, stream>>>(p);
+      break;
+    case CLEAR_KIND_NPO:
+      if (a->beta == 1.0f) rowloss_twopass_kernel<CLEAR_KIND_NPO, true, 512><<<grid, 512, 0, stream>>>(p);
+      else                 rowloss_twopass_kernel<CLEAR_KIND_NPO, false, 512><<<grid, 512, 0, stream>>>(p);
+      break;
+    default:
+      return fail(CLEAR_ERR_KIND, "clear_head_rowloss: unknown kind %d", a->kind);
+  }
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_head_count_valid(const int64_t* labels, int64_t n_rows, float* inv_count, void* stream) {
+  if (!labels || !inv_count) return fail(CLEAR_ERR_NULL, "clear_head_count_valid: null pointer");
+  if (n_rows <= 0 || n_rows > (1 << 24)) return fail(CLEAR_ERR_SHAPE, "clear_head_count_valid: n_rows out of range");
+  count_valid_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(labels, n_rows, inv_count);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_head_reduce_rows(const float* loss_rows, int64_t n_rows, float scale, const float* scale_dev, float* out,
+                           int accumulate, void* stream) {
+  if (!loss_rows || !out) return fail(CLEAR_ERR_NULL, "clear_head_reduce_rows: null pointer");
+  if (n_rows <= 0) return fail(CLEAR_ERR_SHAPE, "clear_head_reduce_rows: n_rows <= 0");
+  reduce_rows_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(loss_rows, n_rows, scale, scale_dev, out, accumulate);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_head_reduce_sequences(const float* loss_rows, int64_t n_seqs, int64_t rows_per_seq, float* seq_sums,
+                                void* stream) {
+  if (!loss_rows || !seq_sums) return fail(CLEAR_ERR_NULL, "clear_head_reduce_sequences: null pointer");
+  if (n_seqs <= 0 || rows_per_seq <= 0 || n_seqs > INT32_MAX) return fail(CLEAR_ERR_SHAPE, "clear_head_reduce_sequences: bad sizes");
+  reduce_sequences_kernel<<<(unsigned)n_seqs, 256, 0, static_cast<cudaStream_t>(stream)>>>(loss_rows, rows_per_seq, seq_sums);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
+  if (!a) return fail(CLEAR_ERR_NULL, "clear_head_backward: args is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a->dlogits) return fail(CLEAR_ERR_NULL, "clear_head_backward: dlogits is NULL");
+  if (a->n_rows <= 0 || a->n_rows > INT32_MAX || a->hidden_dim <= 0 || a->vocab <= 0)
+    return fail(CLEAR_ERR_SHAPE, "clear_head_backward: bad sizes");
+  if (a->hidden_dim % 8) return fail(CLEAR_ERR_SHAPE, "clear_head_backward: hidden_dim must be a multiple of 8");
+  int rc;
+  if (a->dhidden) {
+    if (!a->weight) return fail(CLEAR_ERR_NULL, "clear_head_backward: dhidden requested but weight is NULL");
+    // dH[n, h] = sum_v dZ[n, v] W[v, h]: A = dZ (K-major, K = vocab), B = W read MN-major.
+    GemmOperand A{a->dlogits, a->dlogits_ld, kMajorK};
+    GemmOperand B{a->weight, a->weight_ld, kMajorMN};
+    rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden, 0, a->dhidden_ld, (int)a->n_rows, a->hidden_dim, a->vocab,
+                          nullptr, 0, /*raster_m_fast=*/0, stream);
+    if (rc) return rc;
+  }
+  if (a->dweight) {
+    if (!a->hidden) return fail(CLEAR_ERR_NULL, "clear_head_backward: dweight requested but hidden is NULL");
+    if (a->accumulate && !a->dweight_f32) return fail(CLEAR_ERR_KIND, "clear_head_backward: accumulate needs fp32 dweight");
+    // dW[v, h] = sum_n dZ[n, v] H[n, h]: both operands read MN-major (K = rows).
+    GemmOperand A{a->dlogits, a->dlogits_ld, kMajorMN};
+    GemmOperand B{a->hidden, a->hidden_ld, kMajorMN};
+    rc = launch_gemm_bf16(a->cta_group, A, B, a->dweight, a->dweight_f32, a->dweight_ld, a->vocab, a->hidden_dim,
+                          (int)a->n_rows, nullptr, a->accumulate, /*raster_m_fast=*/0, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

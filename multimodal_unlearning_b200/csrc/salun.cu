@@ -1,0 +1,481 @@
+// SalUn gradient-saliency mask and the masked AdamW update (HBM-bound byte/integer work).
+//
+// Reference: methods/salun/generate_mask.py:17-89 (`save_gradient_ratio`):
+//   :41-44  gradients[name] += param.grad            -> saliency_accumulate  (bf16 += bf16)
+//   :47-49  abs_().cpu().to(float16)                  -> sal_key(): the fp16 bit pattern of |g|
+//   :61-78  per tensor: sort descending, top int(th*numel) -> 1 (int8)
+//                                                     -> histogram over the 32768 non-negative fp16
+//                                                        patterns, select the k-th largest pattern and
+//                                                        the tie budget, write the mask
+// Order statistics over fp16 keys need no sort: non-negative fp16 bit patterns order like the values,
+// so the k-th largest element is found from a 32768-bin histogram, and the reference's stable tie
+// rule (lowest flat index first among equal keys) is an exclusive scan over "== tau".
+// The masked update is the upstream SalUn semantic `grad *= mask` followed by AdamW
+// in torch's `_single_tensor_adam` operation order; fp32 arithmetic is spelled with explicit
+// round-to-nearest intrinsics so that no FMA contraction can change a bit relative to the oracle.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.h"
+
+namespace clear {
+namespace {
+
+constexpr int kBins = 32768;
+constexpr int kChunk = 8192;        // elements per mask chunk (256 threads x 4 vectors x 8)
+constexpr int kChunkThreads = 256;
+constexpr int kChunkIters = kChunk / (kChunkThreads * 8);
+
+__device__ __forceinline__ uint32_t sal_key(__nv_bfloat16 x) {
+  const float f = fabsf(__bfloat162float(x));
+  return (uint32_t)__half_as_ushort(__float2half_rn(f)) & 0x7FFFu;
+}
+
+__device__ __forceinline__ void keys8(const uint4& raw, uint32_t (&k)[8]) {
+  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k[j] = sal_key(h[j]);
+}
+
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) accumulate_kernel(__nv_bfloat16* acc, const __nv_bfloat16* grad, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    uint4 a = reinterpret_cast<const uint4*>(acc)[v];
+    const uint4 g = ld_stream(reinterpret_cast<const uint4*>(grad) + v);
+    __nv_bfloat162* ah = reinterpret_cast<__nv_bfloat162*>(&a);
+    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // torch's bf16 add: operands widened to fp32, added, rounded to nearest-even bf16
+      const float2 x = __bfloat1622float2(ah[j]), y = __bfloat1622float2(gh[j]);
+      ah[j] = __floats2bfloat162_rn(__fadd_rn(x.x, y.x), __fadd_rn(x.y, y.y));
+    }
+    reinterpret_cast<uint4*>(acc)[v] = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t i = nvec << 3; i < n; ++i)
+      acc[i] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(acc[i]), __bfloat162float(grad[i])));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Histogram: each CTA owns a contiguous slice of the flat buffer and a private 32768-bin histogram in
+// shared memory (128 KB); it flushes (sparse global atomics) whenever the slice crosses into the next
+// tensor and at the end.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_segment(const int64_t* off, int n_segs, int64_t pos) {
+  int lo = 0, hi = n_segs - 1;  // largest s with off[s] <= pos
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (off[mid] <= pos) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(512) histogram_kernel(const __nv_bfloat16* acc, const int64_t* seg_off, int n_segs,
+                                                        int64_t n_total, int64_t per_block, uint32_t* hist) {
+  extern __shared__ uint32_t sh[];
+  for (int b = threadIdx.x; b < kBins; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  int64_t pos = (int64_t)blockIdx.x * per_block;
+  const int64_t end = min(pos + per_block, n_total);
+  if (pos >= end) return;
+  int seg = find_segment(seg_off, n_segs, pos);
+  while (pos < end) {
+    while (seg_off[seg + 1] <= pos) ++seg;  // skips empty tensors
+    const int64_t stop = min(end, seg_off[seg + 1]);
+    const int64_t v1 = stop >> 3;
+    for (int64_t v = (pos >> 3) + threadIdx.x; v < v1; v += blockDim.x) {
+      const uint4 raw = ld_stream(reinterpret_cast<const uint4*>(acc) + v);
+      uint32_t k[8];
+      keys8(raw, k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sh[k[j]], 1u);
+    }
+    __syncthreads();
+    uint32_t* out = hist + (size_t)seg * kBins;
+    for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
+      const uint32_t c = sh[b];
+      if (c) { atomicAdd(&out[b], c); sh[b] = 0; }
+    }
+    __syncthreads();
+    pos = stop;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Select: one CTA per tensor.  Descending cumulative counts over the bins; for every threshold the bin
+// tau with  #{key > tau} < k <= #{key >= tau}  and ties = k - #{key > tau}.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxThresholds = 16;
+struct SelectTargets {
+  double th[kMaxThresholds];
+  int n;
+};
+
+__global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, const int64_t* seg_off, SelectTargets tg,
+                                                      int64_t* select) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long wbase[32];
+  const int seg = blockIdx.x;
+  const int64_t numel = seg_off[seg + 1] - seg_off[seg];
+  const uint32_t* h = hist + (size_t)seg * kBins;
+  // thread t owns the 32 bins [hi-31, hi], hi = 32767 - 32 t  (descending order)
+  const int hi = kBins - 1 - 32 * (int)threadIdx.x;
+  unsigned long long local = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) local += h[hi - i];
+  // exclusive scan of `local` across the block, in thread order
+  unsigned long long incl = local;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long v = wsum[lane], s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += u;
+    }
+    wbase[lane] = s - v;
+  }
+  __syncthreads();
+  const unsigned long long above0 = wbase[warp] + incl - local;  // #{key > hi}
+  for (int j = 0; j < tg.n; ++j) {
+    // Python: int(threshold * num_elements) — a double product, truncated (generate_mask.py:69)
+    const long long k = (long long)(tg.th[j] * (double)numel);
+    int64_t* out = select + ((size_t)seg * tg.n + j) * 2;
+    if (k <= 0) {
+      if (threadIdx.x == 0) { out[0] = -1; out[1] = 0; }
+      continue;
+    }
+    if ((unsigned long long)k > above0 && (unsigned long long)k <= above0 + local) {
+      unsigned long long above = above0;
+      for (int i = 0; i < 32; ++i) {
+        const unsigned long long c = h[hi - i];
+        if ((unsigned long long)k <= above + c) { out[0] = hi - i; out[1] = (int64_t)((unsigned long long)k - above); break; }
+        above += c;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mask.  Chunks of 8192 elements never straddle tensors (chunk_prefix[s] = number of chunks before
+// tensor s).  Flat order inside a chunk is (iter, thread, lane-in-vector), loads stay coalesced.
+// ------------------------------------------------------------------------------------------------
+struct ChunkLoc {
+  int seg;
+  int64_t begin, end;  // element range of this chunk
+};
+__device__ __forceinline__ ChunkLoc locate_chunk(const int64_t* seg_off, const int64_t* chunk_prefix, int n_segs) {
+  const int64_t c = blockIdx.x;
+  int lo = 0, hi = n_segs - 1;  // largest s with chunk_prefix[s] <= c
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
+  }
+  ChunkLoc L;
+  L.seg = lo;
+  L.begin = seg_off[lo] + (c - chunk_prefix[lo]) * kChunk;
+  L.end = min(L.begin + (int64_t)kChunk, seg_off[lo + 1]);
+  return L;
+}
+
+__global__ void __launch_bounds__(kChunkThreads) tie_count_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
+                                                                  const int64_t* chunk_prefix, int n_segs,
+                                                                  const int64_t* select, int n_th, int th_index,
+                                                                  uint32_t* tie_count) {
+  __shared__ uint32_t red[kChunkThreads / 32];
+  const ChunkLoc L = locate_chunk(seg_off, chunk_prefix, n_segs);
+  const int64_t tau = select[((size_t)L.seg * n_th + th_index) * 2];
+  uint32_t cnt = 0;
+  if (tau >= 0) {
+#pragma unroll
+    for (int it = 0; it < kChunkIters; ++it) {
+      const int64_t e = L.begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
+      if (e < L.end) {
+        uint32_t k[8];
+        keys8(ld_stream(acc + e), k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cnt += (k[j] == (uint32_t)tau);
+      }
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kChunkThreads / 32; ++w) t += red[w];
+    tie_count[blockIdx.x] = t;
+  }
+}
+
+// In-place exclusive scan of the chunk tie counts of each tensor (one CTA per tensor).  Counts are
+// clamped so a 32-bit prefix cannot overflow: a prefix beyond the tie budget selects nothing anyway.
+__global__ void __launch_bounds__(1024) tie_scan_kernel(const int64_t* chunk_prefix, uint32_t* tie_count) {
+  __shared__ unsigned long long carry;
+  __shared__ unsigned long long wsum[32];
+  const int64_t c0 = chunk_prefix[blockIdx.x], c1 = chunk_prefix[blockIdx.x + 1];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = c0; base < c1; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const unsigned long long v = (i < c1) ? tie_count[i] : 0;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long wb = 0;
+    for (int w = 0; w < warp; ++w) wb += wsum[w];
+    const unsigned long long excl = carry + wb + incl - v;
+    if (i < c1) tie_count[i] = (uint32_t)min(excl, (unsigned long long)0xFFFFFFFFull);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kChunkThreads) mask_write_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
+                                                                   const int64_t* chunk_prefix, int n_segs,
+                                                                   const int64_t* select, int n_th, int th_index,
+                                                                   const uint32_t* tie_prefix, int8_t* mask) {
+  __shared__ uint32_t wcnt[kChunkIters][kChunkThreads / 32];
+  const ChunkLoc L = locate_chunk(seg_off, chunk_prefix, n_segs);
+  const int64_t* sel = select + ((size_t)L.seg * n_th + th_index) * 2;
+  const int64_t tau = sel[0];
+  const unsigned long long budget = (unsigned long long)sel[1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  uint32_t k[kChunkIters][8];
+  uint32_t mine[kChunkIters];   // ties held by this thread per iteration
+  uint32_t before[kChunkIters]; // ties in lower lanes of this warp, same iteration
+#pragma unroll
+  for (int it = 0; it < kChunkIters; ++it) {
+    const int64_t e = L.begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
+    mine[it] = 0;
+    if (e < L.end) {
+      keys8(ld_stream(acc + e), k[it]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[it] += (tau >= 0 && k[it][j] == (uint32_t)tau);
+    }
+    uint32_t incl = mine[it];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    before[it] = incl - mine[it];
+    if (lane == 31) wcnt[it][warp] = incl;
+  }
+  __syncthreads();
+  unsigned long long run = tie_prefix[blockIdx.x];  // ties of this tensor in earlier chunks
+#pragma unroll
+  for (int it = 0; it < kChunkIters; ++it) {
+    unsigned long long rank = run + before[it];
+    for (int w = 0; w < kChunkThreads / 32; ++w) {
+      if (w < warp) rank += wcnt[it][w];
+      run += wcnt[it][w];
+    }
+    const int64_t e = L.begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
+    if (e < L.end) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t bit;
+        if (tau < 0) bit = 0;
+        else if (k[it][j] > (uint32_t)tau) bit = 1;
+        else if (k[it][j] == (uint32_t)tau) { bit = (rank < budget) ? 1u : 0u; ++rank; }
+        else bit = 0;
+        if (j < 4) lo |= bit << (8 * j); else hi |= bit << (8 * (j - 4));
+      }
+      *reinterpret_cast<uint2*>(mask + e) = make_uint2(lo, hi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// masked AdamW
+// ------------------------------------------------------------------------------------------------
+struct AdamConsts {
+  float decay;      // 1 - lr * weight_decay
+  float w1;         // 1 - beta1
+  float beta2, w2;  // beta2, 1 - beta2
+  float bc2_sqrt;   // sqrt(1 - beta2^step)
+  float step_size;  // lr / (1 - beta1^step)
+  float eps;
+};
+
+__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamConsts& c) {
+  p = __fmul_rn(p, c.decay);                                        // param.mul_(1 - lr * wd)
+  m = __fadd_rn(m, __fmul_rn(c.w1, __fsub_rn(g, m)));               // exp_avg.lerp_(grad, 1 - beta1)
+  v = __fadd_rn(__fmul_rn(v, c.beta2), __fmul_rn(c.w2, __fmul_rn(g, g)));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
+  return __fsub_rn(p, __fmul_rn(c.step_size, __fdiv_rn(m, denom)));   // addcdiv_(exp_avg, denom, -step_size)
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const __nv_bfloat16* grad, float* exp_avg,
+                                                    float* exp_avg_sq, const int8_t* mask, int64_t n, AdamConsts c) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 pr = reinterpret_cast<const uint4*>(param)[i];
+    const uint4 gr = ld_stream(reinterpret_cast<const uint4*>(grad) + i);
+    float4 m0 = reinterpret_cast<const float4*>(exp_avg)[2 * i], m1 = reinterpret_cast<const float4*>(exp_avg)[2 * i + 1];
+    float4 v0 = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i], v1 = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i + 1];
+    uint2 mk = make_uint2(0x01010101u, 0x01010101u);
+    if (mask) mk = *reinterpret_cast<const uint2*>(mask + (i << 3));
+    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(&pr);
+    const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&gr);
+    float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t mb = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xFFu;
+      const float g = mb ? __bfloat162float(gh[j]) : 0.f;  // grad *= mask
+      ph[j] = __float2bfloat16_rn(adam_one(__bfloat162float(ph[j]), g, mm[j], vv[j], c));
+    }
+    reinterpret_cast<uint4*>(param)[i] = pr;
+    reinterpret_cast<float4*>(exp_avg)[2 * i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(exp_avg)[2 * i + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
+    reinterpret_cast<float4*>(exp_avg_sq)[2 * i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(exp_avg_sq)[2 * i + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t i = nvec << 3; i < n; ++i) {
+      const float g = (!mask || mask[i]) ? __bfloat162float(grad[i]) : 0.f;
+      param[i] = __float2bfloat16_rn(adam_one(__bfloat162float(param[i]), g, exp_avg[i], exp_avg_sq[i], c));
+    }
+  }
+}
+
+int stream_grid(int64_t nvec, int threads) {
+  const int sms = device_sm_count();
+  int64_t blocks = (nvec + threads - 1) / threads;
+  const int64_t cap = (int64_t)(sms > 0 ? sms : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+}  // namespace clear
+
+using namespace clear;
+
+extern "C" {
+
+int clear_saliency_accumulate(void* acc, const void* grad, int64_t n, void* stream) {
+  if (!acc || !grad) return fail(CLEAR_ERR_NULL, "clear_saliency_accumulate: null pointer");
+  if (n <= 0) return fail(CLEAR_ERR_SHAPE, "clear_saliency_accumulate: n <= 0");
+  if ((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(grad)) & 15)
+    return fail(CLEAR_ERR_ALIGN, "clear_saliency_accumulate: pointers must be 16-byte aligned");
+  accumulate_kernel<<<stream_grid(n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(acc), static_cast<const __nv_bfloat16*>(grad), n);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, int32_t n_segs, int64_t n_total,
+                             uint32_t* hist, void* stream) {
+  if (!acc || !seg_offsets_dev || !hist) return fail(CLEAR_ERR_NULL, "clear_saliency_histogram: null pointer");
+  if (n_segs <= 0 || n_total <= 0 || (n_total & 7)) return fail(CLEAR_ERR_SHAPE, "clear_saliency_histogram: n_total must be a positive multiple of 8");
+  if (reinterpret_cast<uintptr_t>(acc) & 15) return fail(CLEAR_ERR_ALIGN, "clear_saliency_histogram: acc must be 16-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    CLEAR_CUDA_OK(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBins * 4));
+    configured = true;
+  }
+  const int sms = device_sm_count();
+  int64_t blocks = sms > 0 ? sms : 148;
+  int64_t per_block = ((n_total + blocks - 1) / blocks + 4095) / 4096 * 4096;
+  blocks = (n_total + per_block - 1) / per_block;
+  histogram_kernel<<<(unsigned)blocks, 512, kBins * 4, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(acc), seg_offsets_dev, n_segs, n_total, per_block, hist);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, int32_t n_segs,
+                          const double* thresholds_host, int32_t n_th, int64_t* select, void* stream) {
+  if (!hist || !seg_offsets_dev || !thresholds_host || !select) return fail(CLEAR_ERR_NULL, "clear_saliency_select: null pointer");
+  if (n_segs <= 0 || n_th <= 0 || n_th > kMaxThresholds) return fail(CLEAR_ERR_SHAPE, "clear_saliency_select: 1 <= n_th <= %d", kMaxThresholds);
+  SelectTargets tg;
+  tg.n = n_th;
+  for (int j = 0; j < n_th; ++j) tg.th[j] = thresholds_host[j];
+  select_kernel<<<(unsigned)n_segs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(hist, seg_offsets_dev, tg, select);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int64_t clear_saliency_chunk_elems(void) { return kChunk; }
+
+int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
+                        int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
+                        uint32_t* tie_scratch, int8_t* mask, void* stream_) {
+  if (!acc || !seg_offsets_dev || !chunk_prefix_dev || !select || !tie_scratch || !mask)
+    return fail(CLEAR_ERR_NULL, "clear_saliency_mask: null pointer");
+  if (n_segs <= 0 || n_chunks <= 0 || n_chunks > INT32_MAX || th_index < 0 || th_index >= n_th)
+    return fail(CLEAR_ERR_SHAPE, "clear_saliency_mask: bad sizes");
+  if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(mask) & 7))
+    return fail(CLEAR_ERR_ALIGN, "clear_saliency_mask: acc must be 16-byte and mask 8-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(acc);
+  tie_count_kernel<<<(unsigned)n_chunks, kChunkThreads, 0, stream>>>(a, seg_offsets_dev, chunk_prefix_dev, n_segs, select,
+                                                                    n_th, th_index, tie_scratch);
+  tie_scan_kernel<<<(unsigned)n_segs, 1024, 0, stream>>>(chunk_prefix_dev, tie_scratch);
+  mask_write_kernel<<<(unsigned)n_chunks, kChunkThreads, 0, stream>>>(a, seg_offsets_dev, chunk_prefix_dev, n_segs, select,
+                                                                     n_th, th_index, tie_scratch, mask);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_masked_adamw(const ClearAdamWArgs* a, void* stream) {
+  if (!a) return fail(CLEAR_ERR_NULL, "clear_masked_adamw: args is NULL");
+  if (!a->param || !a->grad || !a->exp_avg || !a->exp_avg_sq) return fail(CLEAR_ERR_NULL, "clear_masked_adamw: null tensor");
+  if (a->n <= 0 || a->step < 1) return fail(CLEAR_ERR_SHAPE, "clear_masked_adamw: n > 0 and step >= 1 required");
+  if ((reinterpret_cast<uintptr_t>(a->param) | reinterpret_cast<uintptr_t>(a->grad) | reinterpret_cast<uintptr_t>(a->exp_avg) |
+       reinterpret_cast<uintptr_t>(a->exp_avg_sq)) & 15)
+    return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: tensors must be 16-byte aligned");
+  if (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)) return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: mask must be 8-byte aligned");
+  // Scalar prologue of torch.optim.adam._single_tensor_adam, in double like the Python floats there.
+  AdamConsts c;
+  c.decay = (float)(1.0 - a->lr * a->weight_decay);
+  c.w1 = (float)(1.0 - a->beta1);
+  c.beta2 = (float)a->beta2;
+  c.w2 = (float)(1.0 - a->beta2);
+  const double bc1 = 1.0 - pow(a->beta1, (double)a->step);
+  const double bc2 = 1.0 - pow(a->beta2, (double)a->step);
+  c.step_size = (float)(a->lr / bc1);
+  c.bc2_sqrt = (float)sqrt(bc2);
+  c.eps = (float)a->eps;
+  adamw_kernel<<<stream_grid(a->n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(a->param), static_cast<const __nv_bfloat16*>(a->grad), a->exp_avg, a->exp_avg_sq,
+      a->mask, a->n, c);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
