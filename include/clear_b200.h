@@ -101,6 +101,10 @@ typedef struct ClearProjectArgs {
   int32_t cta_group;
 } ClearProjectArgs;
 int clear_head_project(const ClearProjectArgs* args, void* stream);
+/* Same statistics for teacher logits handed over already materialised (`self.teacher_model(**x).logits`,
+ * mm/trainer.py:199-200): lse_part float2 [n_rows][clear_head_vtiles(vocab)] from bf16 logits. */
+int clear_head_lse_partials(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Loss head, stage 2 — row-wise loss and d(loss)/d(logits), written in place over the logits.
@@ -176,9 +180,10 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
 /* For each segment and each of n_th thresholds: k = (int64)(th * numel) (double product truncated,
  * as Python int()); finds tau = bit pattern of the k-th largest value and the number of ties to
  * take.  select: int64 [n_segs][n_th][2] = (tau_bits or -1 when k == 0, ties_to_take).
- * thresholds: host doubles. */
-int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, int32_t n_segs,
-                          const double* thresholds_host, int32_t n_th, int64_t* select, void* stream);
+ * seg_numel_dev: optional device int64 [n_segs] true element counts for tensors stored zero-padded
+ * to the next multiple of 8 (NULL: numel = offset difference).  thresholds: host doubles. */
+int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, const int64_t* seg_numel_dev,
+                          int32_t n_segs, const double* thresholds_host, int32_t n_th, int64_t* select, void* stream);
 /* mask[i] = 1 iff fp16(|acc[i]|) > tau, or == tau and the element is among the first `ties` such
  * elements of its tensor in flat index order (stable descending sort; SURVEY.md §8c tie contract).
  * th_index selects which threshold's (tau, ties) of `select` to use.

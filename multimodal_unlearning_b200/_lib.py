@@ -16,7 +16,7 @@ KIND_CE, KIND_KL_FWD, KIND_KL_REV, KIND_NPO, KIND_ENTROPY = range(5)
 
 EXPORTED_SYMBOLS = (
     "clear_last_error", "clear_abi_version", "clear_device_info", "clear_gemm_bf16", "clear_head_vtiles",
-    "clear_head_project", "clear_head_rowloss", "clear_head_count_valid", "clear_head_reduce_rows",
+    "clear_head_project", "clear_head_lse_partials", "clear_head_rowloss", "clear_head_count_valid", "clear_head_reduce_rows",
     "clear_head_reduce_sequences", "clear_head_backward", "clear_saliency_accumulate",
     "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_chunk_elems", "clear_saliency_mask",
     "clear_masked_adamw",
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.clear_gemm_bf16.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.clear_head_vtiles.argtypes = [C.c_int]
     lib.clear_head_project.argtypes = [C.POINTER(ProjectArgs), C.c_void_p]
+    lib.clear_head_lse_partials.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.clear_head_rowloss.argtypes = [C.POINTER(RowLossArgs), C.c_void_p]
     lib.clear_head_count_valid.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.clear_head_reduce_rows.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -89,7 +90,7 @@ def load() -> C.CDLL:
     lib.clear_head_backward.argtypes = [C.POINTER(BackwardArgs), C.c_void_p]
     lib.clear_saliency_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.clear_saliency_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
-    lib.clear_saliency_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32,
+    lib.clear_saliency_select.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32,
                                           C.c_void_p, C.c_void_p]
     lib.clear_saliency_chunk_elems.argtypes = []
     lib.clear_saliency_chunk_elems.restype = C.c_int64

@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(kThreads) rowloss_ce_kernel(const RowLossParam
   __nv_bfloat16* z = a.logits + row * a.ld;
   const int64_t y = a.labels[row];
   const bool valid = (y != kIgnoreIndex);
+  if (valid && (y < 0 || y >= a.vocab)) {  // torch raises a device-side assert here; be as loud as a kernel can
+    if (threadIdx.x == 0) a.loss_rows[row] = __int_as_float(0x7fc00000);
+    return;
+  }
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   if (!a.write_grad) {
     if (threadIdx.x < 32) {
@@ -264,6 +268,35 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
   }
 }
 
+// (max, sum-exp) partials of already-materialised logits (teacher logits handed over as a tensor), in
+// the [row][256-column tile] layout the projection's epilogue emits.  One warp per tile: a lane holds
+// 8 consecutive columns (one 128-bit load).
+__global__ void __launch_bounds__(256) lse_partials_kernel(const __nv_bfloat16* logits, int64_t ld, int vocab,
+                                                           int n_vtiles, float2* part) {
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* z = logits + row * ld;
+  const int lane = threadIdx.x & 31;
+  for (int t = threadIdx.x >> 5; t < n_vtiles; t += 8) {
+    const int c0 = t * 256 + lane * 8;
+    float x[8];
+    if (c0 + 8 <= vocab) {
+      unpack8(*reinterpret_cast<const uint4*>(z + c0), x);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (c0 + j < vocab) ? __bfloat162float(z[c0 + j]) : -INFINITY;
+    }
+    float m = x[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) m = fmaxf(m, x[j]);
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += ptx::ex2_approx((x[j] - m) * kLog2e);
+    s = warp_sum(s);
+    if (lane == 0) part[row * n_vtiles + t] = make_float2(m, s);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // small reductions
 // ---------------------------------------------------------------------------------------------------
@@ -319,6 +352,19 @@ int clear_head_project(const ClearProjectArgs* a, void* stream) {
   GemmOperand B{a->weight, a->weight_ld, kMajorK};
   return launch_gemm_bf16(a->cta_group, A, B, a->logits, 0, a->logits_ld, (int)a->n_rows, a->vocab, a->hidden_dim,
                           a->lse_part, 0, /*raster_m_fast=*/1, static_cast<cudaStream_t>(stream));
+}
+
+int clear_head_lse_partials(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
+                            void* stream) {
+  if (!logits || !lse_part) return fail(CLEAR_ERR_NULL, "clear_head_lse_partials: null pointer");
+  if (n_rows <= 0 || n_rows > INT32_MAX || vocab <= 0 || logits_ld < vocab || logits_ld % 8)
+    return fail(CLEAR_ERR_SHAPE, "clear_head_lse_partials: bad sizes");
+  if (reinterpret_cast<uintptr_t>(logits) & 15) return fail(CLEAR_ERR_ALIGN, "clear_head_lse_partials: logits must be 16-byte aligned");
+  lse_partials_kernel<<<(unsigned)n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(logits), logits_ld, vocab, clear_head_vtiles(vocab),
+      reinterpret_cast<float2*>(lse_part));
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {

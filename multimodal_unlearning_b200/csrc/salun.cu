@@ -124,18 +124,23 @@ struct SelectTargets {
   int n;
 };
 
-__global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, const int64_t* seg_off, SelectTargets tg,
-                                                      int64_t* select) {
+__global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, const int64_t* seg_off,
+                                                      const int64_t* seg_numel, SelectTargets tg, int64_t* select) {
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned long long wbase[32];
   const int seg = blockIdx.x;
-  const int64_t numel = seg_off[seg + 1] - seg_off[seg];
+  // Tensors whose numel is not a multiple of 8 are stored zero-padded up to the next offset: the
+  // padding was histogrammed into bin 0 and is taken out again here.
+  const int64_t extent = seg_off[seg + 1] - seg_off[seg];
+  const int64_t numel = seg_numel ? seg_numel[seg] : extent;
+  const unsigned long long pad = (unsigned long long)(extent - numel);
   const uint32_t* h = hist + (size_t)seg * kBins;
   // thread t owns the 32 bins [hi-31, hi], hi = 32767 - 32 t  (descending order)
   const int hi = kBins - 1 - 32 * (int)threadIdx.x;
   unsigned long long local = 0;
 #pragma unroll 8
   for (int i = 0; i < 32; ++i) local += h[hi - i];
+  if (hi - 31 == 0) local -= pad;
   // exclusive scan of `local` across the block, in thread order
   unsigned long long incl = local;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -159,7 +164,8 @@ __global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, cons
   const unsigned long long above0 = wbase[warp] + incl - local;  // #{key > hi}
   for (int j = 0; j < tg.n; ++j) {
     // Python: int(threshold * num_elements) — a double product, truncated (generate_mask.py:69)
-    const long long k = (long long)(tg.th[j] * (double)numel);
+    long long k = (long long)(tg.th[j] * (double)numel);
+    if (k > numel) k = numel;  // indices[:k] clamps
     int64_t* out = select + ((size_t)seg * tg.n + j) * 2;
     if (k <= 0) {
       if (threadIdx.x == 0) { out[0] = -1; out[1] = 0; }
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, cons
     if ((unsigned long long)k > above0 && (unsigned long long)k <= above0 + local) {
       unsigned long long above = above0;
       for (int i = 0; i < 32; ++i) {
-        const unsigned long long c = h[hi - i];
+        const unsigned long long c = h[hi - i] - ((hi - i) == 0 ? pad : 0ull);
         if ((unsigned long long)k <= above + c) { out[0] = hi - i; out[1] = (int64_t)((unsigned long long)k - above); break; }
         above += c;
       }
@@ -418,14 +424,14 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
   return 0;
 }
 
-int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, int32_t n_segs,
-                          const double* thresholds_host, int32_t n_th, int64_t* select, void* stream) {
+int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, const int64_t* seg_numel_dev,
+                          int32_t n_segs, const double* thresholds_host, int32_t n_th, int64_t* select, void* stream) {
   if (!hist || !seg_offsets_dev || !thresholds_host || !select) return fail(CLEAR_ERR_NULL, "clear_saliency_select: null pointer");
   if (n_segs <= 0 || n_th <= 0 || n_th > kMaxThresholds) return fail(CLEAR_ERR_SHAPE, "clear_saliency_select: 1 <= n_th <= %d", kMaxThresholds);
   SelectTargets tg;
   tg.n = n_th;
   for (int j = 0; j < n_th; ++j) tg.th[j] = thresholds_host[j];
-  select_kernel<<<(unsigned)n_segs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(hist, seg_offsets_dev, tg, select);
+  select_kernel<<<(unsigned)n_segs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(hist, seg_offsets_dev, seg_numel_dev, tg, select);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,372 @@
+"""The fused loss head: lm_head projection + row-wise loss + backward, over the C ABI.
+
+Replaces, for one `model(**split)` call of the reference trainers, everything between "the trunk
+produced hidden states" and "autograd filled dH and lm_head.weight.grad":
+    nn.Linear lm_head            mm/trainer.py:180,184,188-189,...   (A1)
+    HF ForCausalLMLoss           outputs.loss                        (A2)
+    logits2probs                 mm/trainer_utils.py:16-21           (A3)
+    kl_div(batchmean)            mm/trainer.py:203-208,237-242       (A4, A5)
+    NPO ratio                    mm/trainer.py:348-353               (A6)
+    entropy                      mm/trainer.py:195-196               (A6b)
+    get_batch_loss               mm/trainer_utils.py:73-81           (A6c)
+(IDs: SURVEY.md §8a.)  The reference materialises 2-6 fp32 `[B*T, V]` tensors per loss; here rows are
+streamed in blocks of `block_rows`: one bf16 `[block_rows, V]` staging buffer per projected operand is
+the only vocab-wide storage, the projection's epilogue emits the log-sum-exp statistics, one row pass
+turns logits into dlogits in place, and two more tcgen05 contractions consume them.
+
+Everything here runs on the CUDA library; there is no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import KIND_CE, KIND_ENTROPY, KIND_KL_FWD, KIND_KL_REV, KIND_NPO
+
+IGNORE_INDEX = -100
+KIND_NAMES = {KIND_CE: "ce", KIND_KL_FWD: "kl_fwd", KIND_KL_REV: "kl_rev", KIND_NPO: "npo", KIND_ENTROPY: "entropy"}
+_NEEDS_REF = (KIND_KL_FWD, KIND_KL_REV, KIND_NPO)
+
+# Rows staged per pass.  4096 rows x 32064 bf16 = 263 MB per operand: large enough that the dW
+# contraction (K = block_rows) runs near its peak, small against 180 GB.
+DEFAULT_BLOCK_ROWS = 4096
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def shift_labels(labels: torch.Tensor) -> torch.Tensor:
+    """Row (b, t) is scored against labels[b, t+1]; the last row of each sequence is ignored
+    (HF ForCausalLMLoss: pad one -100 on the right, drop the first).  [B, T] -> [B*T] int64."""
+    y = torch.nn.functional.pad(labels, (0, 1), value=IGNORE_INDEX)[..., 1:]
+    return y.reshape(-1).contiguous()
+
+
+def _check_2d_bf16(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the CLEAR loss head has no CPU path")
+    if t.dtype != torch.bfloat16:
+        raise RuntimeError(f"{name} must be bfloat16, got {t.dtype}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"{name} must be a 2-D row-major tensor, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t
+
+
+# --------------------------------------------------------------------------------------------------
+# thin wrappers of the three stages (one C call each)
+# --------------------------------------------------------------------------------------------------
+def vtiles(vocab: int) -> int:
+    return _lib.load().clear_head_vtiles(vocab)
+
+
+def project(hidden: torch.Tensor, weight: torch.Tensor, logits: torch.Tensor, lse_part: torch.Tensor,
+            cta_group: int = 0) -> None:
+    """logits[:, :V] = hidden @ weight.T (bf16) and per-(row, 256-column tile) (max, sum-exp)."""
+    lib = _lib.load()
+    n, h = hidden.shape
+    v = weight.shape[0]
+    a = _lib.ProjectArgs(hidden=hidden.data_ptr(), weight=weight.data_ptr(), logits=logits.data_ptr(),
+                         lse_part=lse_part.data_ptr(), hidden_ld=hidden.stride(0), weight_ld=weight.stride(0),
+                         logits_ld=logits.stride(0), n_rows=n, hidden_dim=h, vocab=v, cta_group=cta_group)
+    _lib.check(lib.clear_head_project(C.byref(a), _stream()), "clear_head_project")
+
+
+def rowloss(kind: int, logits: torch.Tensor, lse_part: torch.Tensor, loss_rows: torch.Tensor, vocab: int, *,
+            ref_logits: torch.Tensor | None = None, ref_lse_part: torch.Tensor | None = None,
+            labels: torch.Tensor | None = None, row_weight: torch.Tensor | None = None,
+            scale_dev: torch.Tensor | None = None, grad_scale: float = 1.0, beta: float = 1.0,
+            write_grad: bool = True) -> None:
+    lib = _lib.load()
+    a = _lib.RowLossArgs(logits=logits.data_ptr(), lse_part=lse_part.data_ptr(), ref_logits=_ptr(ref_logits),
+                         ref_lse_part=_ptr(ref_lse_part), labels=_ptr(labels), row_weight=_ptr(row_weight),
+                         scale_dev=_ptr(scale_dev), loss_rows=loss_rows.data_ptr(), logits_ld=logits.stride(0),
+                         ref_ld=ref_logits.stride(0) if ref_logits is not None else 0, n_rows=logits.shape[0],
+                         vocab=vocab, kind=kind, grad_scale=grad_scale, beta=beta, write_grad=int(write_grad))
+    _lib.check(lib.clear_head_rowloss(C.byref(a), _stream()), "clear_head_rowloss")
+
+
+def backward(dlogits: torch.Tensor, vocab: int, hidden: torch.Tensor, weight: torch.Tensor,
+             dhidden: torch.Tensor | None, dweight: torch.Tensor | None, accumulate: bool = False,
+             cta_group: int = 0) -> None:
+    lib = _lib.load()
+    a = _lib.BackwardArgs(dlogits=dlogits.data_ptr(), hidden=hidden.data_ptr(), weight=weight.data_ptr(),
+                          dhidden=_ptr(dhidden), dweight=_ptr(dweight), dlogits_ld=dlogits.stride(0),
+                          hidden_ld=hidden.stride(0), weight_ld=weight.stride(0),
+                          dhidden_ld=dhidden.stride(0) if dhidden is not None else 0,
+                          dweight_ld=dweight.stride(0) if dweight is not None else 0, n_rows=dlogits.shape[0],
+                          hidden_dim=hidden.shape[1], vocab=vocab,
+                          dweight_f32=int(dweight is not None and dweight.dtype == torch.float32),
+                          accumulate=int(accumulate), cta_group=cta_group)
+    _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward")
+
+
+def count_valid(labels: torch.Tensor, inv_count: torch.Tensor) -> None:
+    _lib.check(_lib.load().clear_head_count_valid(labels.data_ptr(), labels.numel(), inv_count.data_ptr(), _stream()),
+               "clear_head_count_valid")
+
+
+def reduce_rows(loss_rows: torch.Tensor, out: torch.Tensor, scale: float, scale_dev: torch.Tensor | None = None,
+                accumulate: bool = False) -> None:
+    _lib.check(_lib.load().clear_head_reduce_rows(loss_rows.data_ptr(), loss_rows.numel(), scale, _ptr(scale_dev),
+                                                  out.data_ptr(), int(accumulate), _stream()),
+               "clear_head_reduce_rows")
+
+
+def reduce_sequences(loss_rows: torch.Tensor, n_seqs: int, seq_sums: torch.Tensor) -> None:
+    _lib.check(_lib.load().clear_head_reduce_sequences(loss_rows.data_ptr(), n_seqs, loss_rows.numel() // n_seqs,
+                                                       seq_sums.data_ptr(), _stream()),
+               "clear_head_reduce_sequences")
+
+
+# --------------------------------------------------------------------------------------------------
+# the fused forward+backward of one head invocation
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class HeadResult:
+    loss: torch.Tensor                 # fp32 [1], already carries `coef` and the reference's normalisation
+    seq_loss: torch.Tensor | None      # fp32 [n_seqs]: per-sequence sums of the unscaled row terms
+    dhidden: torch.Tensor | None       # bf16 [N, H] = d loss / d hidden
+    dweight: torch.Tensor | None       # bf16 [V, H], or the fp32 accumulation buffer that was passed in
+    loss_rows: torch.Tensor            # fp32 [N] unscaled row terms
+    launches: int                      # kernels of libclear_b200 launched by this call
+
+
+def _normalisation(kind: int, reduction: str, n_rows: int, vocab: int, beta: float, n_seqs: int | None):
+    """(loss factor, gradient factor, per_valid): host factors multiplying the summed row terms / the
+    kernel's dterm, and whether 1/#valid (device scalar) also applies.  The two differ only for NPO,
+    whose dterm s - p*sum(s) is the derivative of (1/beta) * sum log(1 + t).
+    Reference semantics: CE mean over non-ignored rows; KL over ALL rows / N;
+    NPO (2/beta) * mean over N*V; entropy raw sum; get_batch_loss per-sequence sums averaged over B."""
+    gfac = beta if kind == KIND_NPO else 1.0
+    if reduction == "sum":
+        return 1.0, gfac, False
+    if reduction == "seq_mean":
+        if not n_seqs:
+            raise ValueError("reduction='seq_mean' needs n_seqs")
+        return 1.0 / n_seqs, gfac / n_seqs, False
+    if reduction != "reference":
+        raise ValueError(f"unknown reduction {reduction!r}")
+    if kind == KIND_CE:
+        return 1.0, 1.0, True
+    if kind in (KIND_KL_FWD, KIND_KL_REV):
+        return 1.0 / n_rows, 1.0 / n_rows, False
+    if kind == KIND_NPO:
+        return 2.0 / (beta * n_rows * vocab), 2.0 / (n_rows * vocab), False
+    if kind == KIND_ENTROPY:
+        return 1.0, 1.0, False
+    raise ValueError(f"unknown kind {kind}")
+
+
+def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, labels: torch.Tensor | None = None,
+                      ref_hidden: torch.Tensor | None = None, ref_weight: torch.Tensor | None = None,
+                      ref_logits: torch.Tensor | None = None, beta: float = 1.0, coef: float = 1.0,
+                      reduction: str = "reference", n_seqs: int | None = None,
+                      row_weight: torch.Tensor | None = None, need_dhidden: bool = True, need_dweight: bool = True,
+                      dweight_accum: torch.Tensor | None = None, block_rows: int | None = None,
+                      cta_group: int = 0) -> HeadResult:
+    """One head invocation: loss = coef * norm * sum_i term_i, plus d loss/d hidden and d loss/d weight.
+
+    hidden [N, H] bf16, weight [V, H] bf16; labels [N] int64 ALREADY SHIFTED (see shift_labels) for CE;
+    the teacher as (ref_hidden [N, H], ref_weight [V, H]) — projected here, block by block, never fully
+    materialised — or as materialised ref_logits [N, >=V] bf16.
+    dweight_accum: optional fp32 [V, H] buffer; dW is ADDED into it (gradient accumulation across
+    splits / micro-batches happens in fp32 inside the contraction's epilogue) and returned as is.
+    need_dhidden = need_dweight = False gives the forward-only mode (no dlogits are written).
+    """
+    lib = _lib.load()
+    hidden = _check_2d_bf16(hidden, "hidden")
+    weight = _check_2d_bf16(weight, "weight")
+    n, h = hidden.shape
+    v = weight.shape[0]
+    if weight.shape[1] != h:
+        raise RuntimeError(f"weight {tuple(weight.shape)} does not match hidden {tuple(hidden.shape)}")
+    if n == 0:
+        raise RuntimeError("head_loss_fwd_bwd: empty batch (N = 0 rows)")
+    dev = hidden.device
+    needs_ref = kind in _NEEDS_REF
+    if kind not in KIND_NAMES:
+        raise ValueError(f"unknown loss kind {kind}")
+    if needs_ref:
+        if ref_logits is None and (ref_hidden is None or ref_weight is None):
+            raise RuntimeError(f"kind {KIND_NAMES[kind]} needs the frozen teacher: pass ref_hidden+ref_weight or ref_logits")
+        if ref_logits is None:
+            ref_hidden = _check_2d_bf16(ref_hidden, "ref_hidden")
+            ref_weight = _check_2d_bf16(ref_weight, "ref_weight")
+            if ref_hidden.shape != hidden.shape or ref_weight.shape != weight.shape:
+                raise RuntimeError("teacher shapes differ from the student's")
+        else:
+            ref_logits = _check_2d_bf16(ref_logits, "ref_logits")
+            if ref_logits.shape[0] != n or ref_logits.shape[1] < v:
+                raise RuntimeError("ref_logits must be [N, >= V]")
+    if kind == KIND_CE:
+        if labels is None:
+            raise RuntimeError("CE needs labels")
+        if labels.dtype != torch.int64 or labels.numel() != n or not labels.is_cuda:
+            raise RuntimeError("labels must be a CUDA int64 tensor with one (shifted) label per row")
+        labels = labels.reshape(-1).contiguous()
+    if row_weight is not None:
+        row_weight = row_weight.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if row_weight.numel() != n:
+            raise RuntimeError("row_weight must have one entry per row")
+
+    write_grad = need_dhidden or need_dweight
+    blk = min(n, block_rows or DEFAULT_BLOCK_ROWS)
+    n_blocks = (n + blk - 1) // blk
+    ld = _round_up(v, 64)
+    nt = vtiles(v)
+    launches = 0
+
+    host_scale, grad_scale, per_valid = _normalisation(kind, reduction, n, v, beta, n_seqs)
+    inv_count = None
+    if per_valid:
+        inv_count = torch.empty(1, dtype=torch.float32, device=dev)
+        count_valid(labels, inv_count)
+        launches += 1
+
+    z = torch.empty((blk, ld), dtype=torch.bfloat16, device=dev)
+    part = torch.empty((blk, nt, 2), dtype=torch.float32, device=dev)
+    zr = rpart = None
+    if needs_ref:
+        rpart = torch.empty((blk, nt, 2), dtype=torch.float32, device=dev)
+        if ref_logits is None:
+            zr = torch.empty((blk, ld), dtype=torch.bfloat16, device=dev)
+    loss_rows = torch.empty(n, dtype=torch.float32, device=dev)
+    dhidden = torch.empty_like(hidden) if need_dhidden else None
+    dweight = None
+    if need_dweight:
+        if dweight_accum is not None:
+            if dweight_accum.dtype != torch.float32 or dweight_accum.shape != weight.shape or not dweight_accum.is_contiguous():
+                raise RuntimeError("dweight_accum must be a contiguous fp32 [V, H] tensor")
+            dweight = dweight_accum
+        elif n_blocks == 1:
+            dweight = torch.empty_like(weight)          # single block: bf16 straight from the epilogue
+        else:
+            dweight = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+
+    for b in range(n_blocks):
+        r0, r1 = b * blk, min(n, (b + 1) * blk)
+        rows = r1 - r0
+        hb = hidden[r0:r1]
+        zb, pb = z[:rows], part[:rows]
+        project(hb, weight, zb, pb, cta_group)
+        launches += 1
+        zrb = rpb = None
+        if needs_ref:
+            rpb = rpart[:rows]
+            if ref_logits is None:
+                zrb = zr[:rows]
+                project(ref_hidden[r0:r1], ref_weight, zrb, rpb, cta_group)
+                launches += 1
+            else:
+                zrb = ref_logits[r0:r1]
+                _ref_lse(zrb, rpb, v)
+                launches += 1
+        rowloss(kind, zb, pb, loss_rows[r0:r1], v, ref_logits=zrb, ref_lse_part=rpb,
+                labels=labels[r0:r1] if labels is not None and kind == KIND_CE else None,
+                row_weight=row_weight[r0:r1] if row_weight is not None else None, scale_dev=inv_count,
+                grad_scale=coef * grad_scale, beta=beta, write_grad=write_grad)
+        launches += 1
+        if write_grad:
+            acc = (dweight_accum is not None) or b > 0
+            backward(zb, v, hb, weight, dhidden[r0:r1] if need_dhidden else None,
+                     dweight if need_dweight else None, accumulate=acc, cta_group=cta_group)
+            launches += int(need_dhidden) + int(need_dweight)
+
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    reduce_rows(loss_rows, loss, coef * host_scale, inv_count)
+    launches += 1
+    seq_loss = None
+    if n_seqs:
+        if n % n_seqs:
+            raise RuntimeError("n_seqs must divide the number of rows")
+        seq_loss = torch.empty(n_seqs, dtype=torch.float32, device=dev)
+        reduce_sequences(loss_rows, n_seqs, seq_loss)
+        launches += 1
+    if need_dweight and dweight_accum is None and dweight.dtype != torch.bfloat16:
+        dweight = dweight.to(torch.bfloat16)
+    del lib
+    return HeadResult(loss, seq_loss, dhidden, dweight, loss_rows, launches)
+
+
+def _ref_lse(ref_logits: torch.Tensor, lse_part: torch.Tensor, vocab: int) -> None:
+    """(max, sum-exp) partials of materialised teacher logits, in the layout the projection emits."""
+    lib = _lib.load()
+    _lib.check(lib.clear_head_lse_partials(ref_logits.data_ptr(), ref_logits.stride(0), ref_logits.shape[0], vocab,
+                                           lse_part.data_ptr(), _stream()), "clear_head_lse_partials")
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd boundary
+# --------------------------------------------------------------------------------------------------
+class _FusedHeadLoss(torch.autograd.Function):
+    """loss = f(hidden, weight).  Forward runs the fused forward+backward (dlogits exist only inside the
+    staging block), backward scales the stored dH / dW by the incoming scalar gradient."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, beta, coef, reduction, n_seqs,
+                row_weight, block_rows):
+        shape = hidden.shape
+        h2 = hidden.reshape(-1, shape[-1])
+        cast = h2.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16
+        hb = h2.to(torch.bfloat16).contiguous()
+        wb = weight.to(torch.bfloat16).contiguous()
+        rh = ref_hidden.reshape(-1, shape[-1]).to(torch.bfloat16).contiguous() if ref_hidden is not None else None
+        rw = ref_weight.to(torch.bfloat16).contiguous() if ref_weight is not None else None
+        rl = ref_logits.reshape(-1, ref_logits.shape[-1]).to(torch.bfloat16).contiguous() if ref_logits is not None else None
+        res = head_loss_fwd_bwd(hb, wb, kind, labels=labels, ref_hidden=rh, ref_weight=rw, ref_logits=rl, beta=beta,
+                                coef=coef, reduction=reduction, n_seqs=n_seqs, row_weight=row_weight,
+                                need_dhidden=ctx.needs_input_grad[0], need_dweight=ctx.needs_input_grad[1],
+                                block_rows=block_rows)
+        dh = res.dhidden.reshape(shape) if res.dhidden is not None else None
+        dw = res.dweight
+        if cast:
+            dh = dh.to(hidden.dtype) if dh is not None else None
+            dw = dw.to(weight.dtype) if dw is not None else None
+        ctx.save_for_backward(dh, dw)
+        ctx.mark_non_differentiable(*( [res.seq_loss] if res.seq_loss is not None else [] ))
+        if res.seq_loss is not None:
+            return res.loss.reshape(()), res.seq_loss
+        return res.loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        dh, dw = ctx.saved_tensors
+        g = g.to(torch.float32)
+        gh = (dh * g.to(dh.dtype)) if dh is not None else None
+        gw = (dw * g.to(dw.dtype)) if dw is not None else None
+        return (gh, gw) + (None,) * 11
+
+
+def fused_head_loss(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, labels: torch.Tensor | None = None,
+                    ref_hidden: torch.Tensor | None = None, ref_weight: torch.Tensor | None = None,
+                    ref_logits: torch.Tensor | None = None, beta: float = 1.0, coef: float = 1.0,
+                    reduction: str = "reference", n_seqs: int | None = None, row_weight: torch.Tensor | None = None,
+                    block_rows: int | None = None):
+    """Differentiable loss of one head invocation.  hidden [..., H]; labels already shifted, flat.
+    Returns a 0-dim fp32 tensor (and the per-sequence sums when n_seqs is given)."""
+    return _FusedHeadLoss.apply(hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, float(beta),
+                                float(coef), reduction, n_seqs, row_weight, block_rows)
+
+
+@torch.no_grad()
+def sequence_nll(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, block_rows: int | None = None):
+    """Forward-only `get_batch_loss` (mm/trainer_utils.py:73-81; used by mm/eval.py:64-92): per-sequence
+    SUM of shifted token CE.  hidden [B, T, H], labels [B, T] (unshifted).  Returns fp32 [B]."""
+    b, t, h = hidden.shape
+    res = head_loss_fwd_bwd(hidden.reshape(b * t, h).to(torch.bfloat16).contiguous(),
+                            weight.to(torch.bfloat16).contiguous(), KIND_CE, labels=shift_labels(labels),
+                            reduction="seq_mean", n_seqs=b, need_dhidden=False, need_dweight=False,
+                            block_rows=block_rows)
+    return res.seq_loss

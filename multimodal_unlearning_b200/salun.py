@@ -1,0 +1,209 @@
+"""SalUn gradient-saliency masks and the masked AdamW update, over the C ABI.
+
+Host-side mirror of methods/salun/generate_mask.py:17-89 (`save_gradient_ratio`):
+    :41-44  gradients[name] += param.grad          -> SaliencyState.accumulate        (bf16 += bf16)
+    :47-49  abs_().cpu().to(float16)               -> keys = fp16 bit pattern of |acc|, formed in-kernel
+    :52-85  per tensor, per threshold: sort desc., top int(th * numel) -> 1 (int8)
+                                                   -> SaliencyState.masks (histogram + select + mask)
+    :87-89  torch.save(dict[name -> int8 mask])    -> save_gradient_ratio writes the same `with_{th}.pt`
+The masked update (`grad *= mask` then AdamW) is MaskedAdamW.
+
+All parameters of a model live in ONE flat bf16 buffer (tensors start at multiples of 8 elements, zero
+padded), so that every stage is a single grid over HBM instead of one launch per tensor.
+There is no CPU path: the reference's CPU sort is replaced by order statistics over the 32768
+non-negative fp16 bit patterns; ties at the threshold value are broken by flat index (stable sort).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Iterator, Sequence
+
+import torch
+
+from . import _lib
+
+REFERENCE_THRESHOLDS = (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)  # generate_mask.py:52
+N_BINS = 32768
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class FlatLayout:
+    """Placement of named tensors in a flat buffer: offsets are multiples of 8 elements (16 B of bf16)."""
+
+    def __init__(self, named_shapes: Sequence[tuple[str, Sequence[int]]]):
+        self.names = [n for n, _ in named_shapes]
+        self.shapes = [tuple(s) for _, s in named_shapes]
+        self.numels = [int(torch.Size(s).numel()) for s in self.shapes]
+        offs = [0]
+        for n in self.numels:
+            offs.append(offs[-1] + (n + 7) // 8 * 8)
+        self.offsets = offs
+        self.total = offs[-1]
+        chunk = int(_lib.load().clear_saliency_chunk_elems())
+        pref = [0]
+        for n in self.numels:
+            pref.append(pref[-1] + ((n + 7) // 8 * 8 + chunk - 1) // chunk)
+        self.chunk_prefix = pref
+        self.n_chunks = pref[-1]
+
+    @classmethod
+    def of_model(cls, model: torch.nn.Module) -> "FlatLayout":
+        return cls([(n, p.shape) for n, p in model.named_parameters()])
+
+    def view(self, flat: torch.Tensor, i: int) -> torch.Tensor:
+        return flat[self.offsets[i]: self.offsets[i] + self.numels[i]].view(self.shapes[i])
+
+    def device_tables(self, device) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        return (torch.tensor(self.offsets, dtype=torch.int64, device=device),
+                torch.tensor(self.numels, dtype=torch.int64, device=device),
+                torch.tensor(self.chunk_prefix, dtype=torch.int64, device=device))
+
+
+class SaliencyState:
+    """The `gradients` dict of save_gradient_ratio as one flat bf16 buffer on the GPU."""
+
+    def __init__(self, layout: FlatLayout, device="cuda"):
+        self.layout = layout
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("SaliencyState lives on a CUDA device: SalUn masks have no CPU path here")
+        self.acc = torch.zeros(layout.total, dtype=torch.bfloat16, device=self.device)
+        self.seg_off, self.seg_numel, self.chunk_prefix = layout.device_tables(self.device)
+        self.launches = 0
+
+    # ---- generate_mask.py:41-44 -------------------------------------------------------------------
+    def accumulate_flat(self, grads: torch.Tensor) -> None:
+        """acc += grads for a flat bf16 gradient buffer in this layout (one launch)."""
+        if grads.dtype != torch.bfloat16 or grads.numel() != self.layout.total or not grads.is_cuda:
+            raise RuntimeError("accumulate_flat: need a CUDA bf16 buffer of layout.total elements")
+        _lib.check(_lib.load().clear_saliency_accumulate(self.acc.data_ptr(), grads.data_ptr(), grads.numel(), _stream()),
+                   "clear_saliency_accumulate")
+        self.launches += 1
+
+    def accumulate_model(self, model: torch.nn.Module) -> None:
+        """gradients[name] += param.grad for every parameter that has a gradient."""
+        lib = _lib.load()
+        params = dict(model.named_parameters())
+        for i, name in enumerate(self.layout.names):
+            g = params[name].grad
+            if g is None or self.layout.numels[i] == 0:
+                continue
+            g = g.detach().to(torch.bfloat16).contiguous().view(-1)
+            if g.data_ptr() % 16:
+                g = g.clone()
+            dst = self.acc[self.layout.offsets[i]:]
+            _lib.check(lib.clear_saliency_accumulate(dst.data_ptr(), g.data_ptr(), g.numel(), _stream()),
+                       "clear_saliency_accumulate")
+            self.launches += 1
+
+    # ---- generate_mask.py:47-85 -------------------------------------------------------------------
+    def select(self, thresholds: Sequence[float] = REFERENCE_THRESHOLDS) -> torch.Tensor:
+        """Per tensor and threshold: (bit pattern of the k-th largest key, ties to take).  int64 [S, n_th, 2]."""
+        lib = _lib.load()
+        lay = self.layout
+        n_segs = len(lay.names)
+        hist = torch.zeros((n_segs, N_BINS), dtype=torch.int32, device=self.device)
+        _lib.check(lib.clear_saliency_histogram(self.acc.data_ptr(), self.seg_off.data_ptr(), n_segs, lay.total,
+                                                hist.data_ptr(), _stream()), "clear_saliency_histogram")
+        th = (C.c_double * len(thresholds))(*[float(t) for t in thresholds])
+        sel = torch.full((n_segs, len(thresholds), 2), -1, dtype=torch.int64, device=self.device)
+        _lib.check(lib.clear_saliency_select(hist.data_ptr(), self.seg_off.data_ptr(), self.seg_numel.data_ptr(), n_segs,
+                                             th, len(thresholds), sel.data_ptr(), _stream()), "clear_saliency_select")
+        self.launches += 2
+        self.hist = hist
+        return sel
+
+    def mask_flat(self, sel: torch.Tensor, th_index: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """int8 mask of one threshold, flat in this layout."""
+        lib = _lib.load()
+        lay = self.layout
+        if out is None:
+            out = torch.empty(lay.total, dtype=torch.int8, device=self.device)
+        scratch = torch.empty(lay.n_chunks, dtype=torch.int32, device=self.device)
+        _lib.check(lib.clear_saliency_mask(self.acc.data_ptr(), self.seg_off.data_ptr(), self.chunk_prefix.data_ptr(),
+                                           len(lay.names), lay.n_chunks, sel.data_ptr(), sel.shape[1], th_index,
+                                           scratch.data_ptr(), out.data_ptr(), _stream()), "clear_saliency_mask")
+        self.launches += 3
+        return out
+
+    def masks(self, thresholds: Sequence[float] = REFERENCE_THRESHOLDS) -> Iterator[tuple[float, dict]]:
+        """Yields (threshold, {name: int8 mask of the parameter's shape}) — `process_threshold`'s hard_dict."""
+        sel = self.select(thresholds)
+        for j, th in enumerate(thresholds):
+            flat = self.mask_flat(sel, j)
+            yield th, {n: self.layout.view(flat, i) for i, n in enumerate(self.layout.names)}
+
+
+def save_gradient_ratio(forget_loader: Iterable, model: torch.nn.Module, criterion, cfg) -> None:
+    """Drop-in for methods/salun/generate_mask.py:17 — same arguments, same `with_{th}.pt` files.
+    `cfg` needs `.save_dir` (unlearn_lr / weight_decay only fed the reference's unused SGD object)."""
+    model.eval()
+    state = SaliencyState(FlatLayout.of_model(model), next(model.parameters()).device)
+    for batch in forget_loader:
+        input_ids, labels, attention_mask = batch[0], batch[1], batch[2]
+        device = state.device
+        loss = model(input_ids=input_ids.to(device), attention_mask=attention_mask.to(device),
+                     labels=labels.to(device)).loss
+        model.zero_grad(set_to_none=True)
+        loss.backward()
+        state.accumulate_model(model)
+    os.makedirs(cfg.save_dir, exist_ok=True)
+    for th, hard_dict in state.masks(REFERENCE_THRESHOLDS):
+        torch.save({k: v.cpu() for k, v in hard_dict.items()}, os.path.join(cfg.save_dir, f"with_{th}.pt"))
+
+
+class MaskedAdamW(torch.optim.Optimizer):
+    """AdamW whose gradient is multiplied by a SalUn mask first (upstream SalUn: `param.grad *= mask[name]`
+    before `optimizer.step()`).  bf16 parameters and gradients, fp32 moments, torch's
+    `_single_tensor_adam` operation order; one fused pass over 23 bytes per parameter."""
+
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, masks: dict | None = None):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.masks = masks or {}  # id(param) or param -> int8 tensor
+
+    def set_mask(self, param: torch.Tensor, mask: torch.Tensor | None) -> None:
+        if mask is None:
+            self.masks.pop(param, None)
+        else:
+            self.masks[param] = mask.to(device=param.device, dtype=torch.int8).contiguous()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        lib = _lib.load()
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if p.dtype != torch.bfloat16 or not p.is_cuda or not p.is_contiguous():
+                    raise RuntimeError("MaskedAdamW updates contiguous CUDA bf16 parameters")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+                    st["exp_avg_sq"] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+                st["step"] += 1
+                g = p.grad.to(torch.bfloat16).contiguous()
+                m = self.masks.get(p)
+                a = _lib.AdamWArgs(param=p.data_ptr(), grad=g.data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
+                                   exp_avg_sq=st["exp_avg_sq"].data_ptr(), mask=m.data_ptr() if m is not None else None,
+                                   n=p.numel(), lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
+                                   weight_decay=group["weight_decay"], step=st["step"])
+                _lib.check(lib.clear_masked_adamw(C.byref(a), _stream()), "clear_masked_adamw")
+        return loss
+
+
+def masked_adamw_flat(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                      mask: torch.Tensor | None, step: int, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
+                      weight_decay=0.01) -> None:
+    """One launch over a flat parameter buffer (the layout of FlatLayout)."""
+    a = _lib.AdamWArgs(param=param.data_ptr(), grad=grad.data_ptr(), exp_avg=exp_avg.data_ptr(),
+                       exp_avg_sq=exp_avg_sq.data_ptr(), mask=mask.data_ptr() if mask is not None else None,
+                       n=param.numel(), lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
+                       step=step)
+    _lib.check(_lib.load().clear_masked_adamw(C.byref(a), _stream()), "clear_masked_adamw")

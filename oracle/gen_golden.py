@@ -1,0 +1,187 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE ONLY; runs in the build container (the reference is not present on the GPU box).
+    python -m oracle.gen_golden            # writes every fixture (about a minute)
+
+Head fixtures (one file per loss type and trainer):
+    reference `compute_loss` + backward on the tiny LLaVA / Llama of BASELINE.json configs[0]
+    (2-layer Llama, hidden 128, vocab 32000; fp32; student = seeded init, teacher = student + noise),
+    with forward pre-hooks on lm_head capturing what reaches the head.  Stored: per student forward
+    the hidden states [B, T, 128] and labels, per teacher forward the hidden states, the loss, dH per
+    student forward, and probes of dW (selected rows, column sums, squared norm).  lm_head weights are
+    regenerated from seeds (oracle.ref_harness.head_weight); their checksums are stored.
+SalUn fixture:
+    reference `save_gradient_ratio` on a 2-layer Llama (hidden 32, vocab 512): per-batch gradients (bf16
+    bit patterns), and the ten masks, from the unmodified code and from the same code with
+    `stable=True` added to its torch.sort call.
+"""
+from __future__ import annotations
+
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import head_oracle as HO
+from . import ref_harness as RH
+
+GOLDEN = Path(__file__).resolve().parents[1] / "tests" / "golden"
+TEACHER_HEAD_SEED = 2
+N_PROBE = 96
+
+MM_LOSSES = list(HO.MM_CALL_ORDER)
+NLP_LOSSES = list(HO.NLP_CALL_ORDER)
+
+
+def teacher_head_weight():
+    g = torch.Generator().manual_seed(TEACHER_HEAD_SEED)
+    return RH.head_weight(1) + 0.01 * torch.randn(RH.VOCAB, RH.HIDDEN, generator=g)
+
+
+def probe_rows(labels: torch.Tensor, seed: int) -> np.ndarray:
+    ids = torch.unique(labels[labels >= 0])[: N_PROBE // 2]
+    g = torch.Generator().manual_seed(seed)
+    rnd = torch.randint(0, RH.VOCAB, (N_PROBE - ids.numel(),), generator=g)
+    return torch.unique(torch.cat([ids, rnd])).numpy()
+
+
+def pack(res: dict, labels: list, names_s: list, names_t: list, rows: np.ndarray, beta: float) -> dict:
+    out = {"loss": res["loss"].double().numpy(), "beta": np.float64(beta),
+           "student_splits": np.array(names_s), "teacher_splits": np.array(names_t), "probe_rows": rows}
+    for i, n in enumerate(names_s):
+        out[f"hidden_{i}"] = res["hidden"][i].float().numpy()
+        dh = res["dhidden"][i]  # None: the forward's result was discarded by the reference (dpo's forget pass)
+        out[f"dhidden_{i}"] = (dh if dh is not None else torch.zeros_like(res["hidden"][i])).float().numpy()
+        out[f"labels_{i}"] = labels[i].numpy()
+    for i, n in enumerate(names_t):
+        out[f"ref_hidden_{i}"] = res["ref_hidden"][i].float().numpy()
+    dw = res["dweight"].double()
+    out["dw_rows"] = dw[rows].float().numpy()
+    out["dw_colsum"] = dw.sum(0).numpy()
+    out["dw_sqnorm"] = (dw * dw).sum().numpy()
+    out["w_checksum"] = RH.head_weight(1).double().abs().sum().numpy()
+    out["wref_checksum"] = teacher_head_weight().double().abs().sum().numpy()
+    return out
+
+
+def gen_mm(length_default: int = 32):
+    student = RH.tiny_llava(0)
+    teacher = RH.perturbed_copy(student, 5)
+    with torch.no_grad():
+        teacher.lm_head.weight.copy_(teacher_head_weight())
+    for lt in MM_LOSSES:
+        length = 256 if lt == "grad_diff_forget_ce_retain_ce" else length_default  # configs[0]: bs 2, seq 256
+        beta = 1.0 if lt in ("grad_diff_forget_ce_retain_ce", "grad_ascent") else 0.7
+        inputs = {"retain": RH.mm_split(2, length, 11), "forget": RH.mm_split(2, length, 12),
+                  "idk": RH.mm_split(2, length, 13)}
+        if lt == "sku":
+            inputs["random"] = RH.mm_split(2, length, 14, k_random=3)
+        names_s, names_t = HO.MM_CALL_ORDER[lt]
+        res = RH.run_mm(lt, student, teacher, {k: dict(v) for k, v in inputs.items()}, beta=beta)
+        assert len(res["hidden"]) == len(names_s), (lt, len(res["hidden"]), names_s)
+        assert len(res["ref_hidden"]) == len(names_t), (lt, len(res["ref_hidden"]), names_t)
+
+        def lab(name):
+            if name.startswith("random"):
+                return inputs["random"]["labels"][:, int(name[6:])]
+            return inputs[name]["labels"]
+
+        labels = [lab(n) for n in names_s]
+        out = pack(res, labels, names_s, names_t, probe_rows(labels[0], 3), beta)
+        np.savez(GOLDEN / f"head_mm_{lt}.npz", **out)
+        print(f"mm  {lt:40s} loss {float(res['loss']):+.6f}")
+
+
+def gen_nlp(length: int = 32):
+    student = RH.tiny_llama(0)
+    teacher = RH.perturbed_copy(student, 5)
+    with torch.no_grad():
+        teacher.lm_head.weight.copy_(teacher_head_weight())
+    for lt in NLP_LOSSES:
+        beta = 0.7 if lt not in ("npo",) else 1.0
+        triples = {"forget": RH.nlp_triple(2, length, 21), "retain": RH.nlp_triple(2, length, 22),
+                   "idk": RH.nlp_triple(2, length, 23)}
+        inputs = [triples["forget"], triples["retain"], triples["idk"]]
+        names_s, names_t = HO.NLP_CALL_ORDER[lt]
+        res = RH.run_nlp(lt, student, teacher, inputs, beta=beta)
+        assert len(res["hidden"]) == len(names_s), (lt, len(res["hidden"]), names_s)
+
+        def lab(name):
+            if name == "forget+retain":
+                return torch.cat([triples["forget"][1], triples["retain"][1]], 0)
+            return triples[name][1]
+
+        labels = [lab(n) for n in names_s]
+        out = pack(res, labels, names_s, names_t, probe_rows(labels[0], 3), beta)
+        np.savez(GOLDEN / f"head_nlp_{lt}.npz", **out)
+        print(f"nlp {lt:40s} loss {float(res['loss']):+.6f}")
+
+
+def gen_salun():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    _, _, _, SALUN = RH.import_reference()
+    torch.manual_seed(3)
+    vocab = 512
+    model = LlamaForCausalLM(LlamaConfig(vocab_size=vocab, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                                         num_attention_heads=2, num_key_value_heads=2)).to(torch.bfloat16)
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for _ in range(3):
+        ids = torch.randint(3, vocab, (4, 24), generator=g)
+        lab = ids.clone()
+        lab[:, :8] = -100
+        batches.append((ids, lab, torch.ones_like(ids), torch.arange(4)))
+
+    # per-batch gradients, exactly as save_gradient_ratio obtains them (:36-44)
+    names = [n for n, _ in model.named_parameters()]
+    per_batch = []
+    model.eval()
+    for ids, lab, att, _ in batches:
+        model.zero_grad(set_to_none=True)
+        model(input_ids=ids, attention_mask=att, labels=lab).loss.backward()
+        per_batch.append({n: p.grad.detach().clone() for n, p in model.named_parameters()})
+
+    def run_reference(stable: bool):
+        real_sort = torch.sort
+        if stable:
+            torch.sort = lambda *a, **kw: real_sort(*a, stable=True, **kw)
+        try:
+            with tempfile.TemporaryDirectory() as d:
+                cfg = types.SimpleNamespace(unlearn_lr=1e-5, weight_decay=0.0, save_dir=d)
+                SALUN.save_gradient_ratio(batches, model, None, cfg)
+                return {th: torch.load(f"{d}/with_{th}.pt") for th in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)}
+        finally:
+            torch.sort = real_sort
+
+    ref_unstable = run_reference(False)
+    ref_stable = run_reference(True)
+    out = {"names": np.array(names), "shapes": np.array([";".join(map(str, per_batch[0][n].shape)) for n in names])}
+    for b, grads in enumerate(per_batch):
+        out[f"grad_{b}"] = np.concatenate([grads[n].reshape(-1).view(torch.int16).numpy() for n in names])
+    for th in ref_stable:
+        flat_s = np.concatenate([ref_stable[th][n].reshape(-1).numpy() for n in names])
+        flat_u = np.concatenate([ref_unstable[th][n].reshape(-1).numpy() for n in names])
+        out[f"mask_stable_{th}"] = np.packbits(flat_s.astype(np.uint8))
+        out[f"mask_unstable_{th}"] = np.packbits(flat_u.astype(np.uint8))
+    np.savez_compressed(GOLDEN / "salun_tiny.npz", **out)
+    n_total = sum(per_batch[0][n].numel() for n in names)
+    print(f"salun: {len(names)} tensors, {n_total} elements, 3 batches, 10 thresholds")
+
+
+def main():
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    which = set(sys.argv[1:]) or {"mm", "nlp", "salun"}
+    if "mm" in which:
+        gen_mm()
+    if "nlp" in which:
+        gen_nlp()
+    if "salun" in which:
+        gen_salun()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+"""CPU: the oracle (oracle/head_oracle.py, oracle/salun_oracle.py) against the fixtures the reference
+itself produced (oracle/gen_golden.py).  This is what pins the oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import head_oracle as HO
+from oracle import salun_oracle as SO
+from tests._golden import GOLDEN, MM_LOSSES, NLP_LOSSES, HeadCase, teacher_head_weight
+from oracle import ref_harness as RH
+
+
+def test_seeded_weights_match_fixture_checksums():
+    z = np.load(GOLDEN / "head_mm_npo.npz")
+    assert abs(RH.head_weight(1).double().abs().sum().item() - float(z["w_checksum"])) < 1e-6
+    assert abs(teacher_head_weight().double().abs().sum().item() - float(z["wref_checksum"])) < 1e-6
+
+
+def _check(case: HeadCase, fn, **kw):
+    student, teacher, w, wr = case.oracle_inputs()
+    loss, dh, dw = HO.loss_and_grads(fn, student, w, teacher=teacher, ref_weight=wr, beta=case.beta,
+                                     loss_type=case.loss_type, **kw)
+    if math.isnan(case.loss):
+        assert math.isnan(loss.item())
+        return
+    assert abs(loss.item() - case.loss) <= 2e-5 * max(1.0, abs(case.loss)), (loss.item(), case.loss)
+    for name, want in zip(case.student_splits, case.dhidden):
+        got = dh[name]
+        got = torch.zeros_like(want) if got is None else got
+        scale = max(want.abs().max().item(), 1e-12)
+        assert (got - want).abs().max().item() <= 2e-4 * scale + 1e-9, (case.loss_type, name)
+    scale = max(case.dw_rows.abs().max().item(), 1e-12)
+    assert (dw[case.probe_rows] - case.dw_rows).abs().max().item() <= 2e-4 * scale
+    # column sums of dW vanish analytically (rows of softmax gradients sum to zero): absolute check
+    assert (dw.double().sum(0) - case.dw_colsum).abs().max().item() <= 1e-3 * case.dw_sqnorm ** 0.5
+    assert abs((dw.double() ** 2).sum().item() - case.dw_sqnorm) <= 1e-3 * case.dw_sqnorm
+
+
+@pytest.mark.parametrize("loss_type", MM_LOSSES)
+def test_mm_oracle_matches_reference(loss_type):
+    _check(HeadCase("mm", loss_type), HO.mm_compute_loss)
+
+
+@pytest.mark.parametrize("loss_type", NLP_LOSSES)
+def test_nlp_oracle_matches_reference(loss_type):
+    _check(HeadCase("nlp", loss_type), HO.nlp_compute_loss)
+
+
+@pytest.mark.parametrize("kind", [HO.KIND_CE, HO.KIND_KL_FWD, HO.KIND_KL_REV, HO.KIND_NPO, HO.KIND_ENTROPY])
+def test_rowloss_closed_forms_match_autograd(kind):
+    """SURVEY.md App. A closed forms (what the CUDA row pass implements) against autograd, fp64."""
+    g = torch.Generator().manual_seed(kind)
+    z = torch.randn(7, 53, generator=g, dtype=torch.float64, requires_grad=True)
+    zr = torch.randn(7, 53, generator=g, dtype=torch.float64)
+    y = torch.randint(0, 53, (7,), generator=g)
+    y[2] = -100
+    beta = 0.7
+    rows, dterm = HO.rowloss(kind, z, zr, y, beta)
+    if kind == HO.KIND_CE:
+        total = torch.nn.functional.cross_entropy(z, y, ignore_index=-100, reduction="sum")
+    elif kind == HO.KIND_KL_FWD:
+        total = HO.kl_batchmean(HO.logits2probs(z), HO.logits2probs(zr)) * 7
+    elif kind == HO.KIND_KL_REV:
+        total = HO.kl_batchmean(HO.logits2probs(zr), HO.logits2probs(z)) * 7
+    elif kind == HO.KIND_NPO:
+        total = HO.npo_mm(z, zr, beta) * (beta * 7 * 53 / 2)
+    else:
+        total = HO.neg_entropy_sum(z)
+    # NPO: rows are log(1 + t); the gradient term s - p sum(s) is d/dz of (1/beta) sum log(1 + t)
+    (total / beta if kind == HO.KIND_NPO else total).backward()
+    assert abs(rows.sum().item() - total.item()) < 1e-10
+    assert (dterm - z.grad).abs().max().item() < 1e-12
+
+
+# ---- SalUn -----------------------------------------------------------------------------------------
+def _salun_fixture():
+    z = np.load(GOLDEN / "salun_tiny.npz")
+    names = [str(n) for n in z["names"]]
+    shapes = [tuple(int(x) for x in str(s).split(";")) for s in z["shapes"]]
+    numels = [int(np.prod(s)) for s in shapes]
+    grads = [torch.from_numpy(z[f"grad_{b}"].copy()).view(torch.bfloat16) for b in range(3)]
+    return z, names, shapes, numels, grads
+
+
+def test_salun_oracle_matches_reference_masks():
+    z, names, shapes, numels, grads = _salun_fixture()
+    acc = grads[0].clone()              # 0 + g
+    for g in grads[1:]:
+        acc = SO.accumulate(acc, g)
+    offs = np.concatenate([[0], np.cumsum(numels)])
+    named = {n: acc[offs[i]:offs[i + 1]].reshape(shapes[i]) for i, n in enumerate(names)}
+    got = SO.masks(named)
+    n_total = int(offs[-1])
+    for th in SO.REFERENCE_THRESHOLDS:
+        flat = np.concatenate([got[th][n].reshape(-1) for n in names])
+        stable = np.unpackbits(z[f"mask_stable_{th}"])[:n_total].astype(np.int8)
+        unstable = np.unpackbits(z[f"mask_unstable_{th}"])[:n_total].astype(np.int8)
+        assert np.array_equal(flat, stable), f"th={th}: differs from the reference (stable sort)"
+        # against the unmodified (unstable) reference: same popcount per tensor, differences only at ties
+        for i, n in enumerate(names):
+            sl = slice(offs[i], offs[i + 1])
+            assert flat[sl].sum() == unstable[sl].sum() == int(th * numels[i])
+            keys = SO.saliency_keys(named[n])
+            tau, _ = SO.select(keys, th)
+            diff = flat[sl] != unstable[sl]
+            assert np.all(keys[diff] == tau)
+
+
+def test_select_agrees_with_sort():
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 40, size=1000).astype(np.uint16)
+    for th in (0.0, 0.001, 0.1, 0.5, 0.999, 1.0):
+        tau, ties = SO.select(keys, th)
+        m = SO.mask_of_keys(keys, th)
+        k = int(th * keys.size)
+        assert m.sum() == k
+        if k:
+            assert (keys[m == 1] >= tau).all() and (keys[m == 0] <= tau).all()
+            assert ((keys == tau) & (m == 1)).sum() == ties
+
+
+def test_adamw_oracle_close_to_torch():
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(4096, generator=g).to(torch.bfloat16)
+    mask = (torch.rand(4096, generator=g) < 0.5).to(torch.int8).numpy()
+    p_ref = torch.nn.Parameter(p0.float().clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, foreach=False)
+    m = np.zeros(4096, np.float32)
+    v = np.zeros(4096, np.float32)
+    p = p0.float()
+    for step in range(1, 4):
+        grad = (0.01 * torch.randn(4096, generator=g)).to(torch.bfloat16)
+        p_ref.grad = grad.float() * torch.from_numpy(mask).float()
+        opt.step()
+        # fp32 master trajectory of the oracle (re-rounding to bf16 each step would hide the comparison)
+        newp, m, v = SO.adamw_step(p.to(torch.bfloat16) if step == 1 else p_bf16, grad, m, v, mask, step, lr=1e-3)
+        p_bf16 = newp
+        if step == 1:
+            assert (newp.float() - p_ref.detach().to(torch.bfloat16).float()).abs().max().item() == 0.0
+    st = opt.state[p_ref]
+    assert np.allclose(m, st["exp_avg"].numpy(), rtol=1e-5, atol=1e-9)
+    assert np.allclose(v, st["exp_avg_sq"].numpy(), rtol=1e-5, atol=1e-12)
