@@ -39,6 +39,43 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class StageTimer:
+    """Optional per-launch timing with CUDA events on the launching stream (bench.py's live roofline
+    measurement).  `with StageTimer() as t: ...; t.summary()` -> {stage: (launches, total ms)}."""
+
+    active: "StageTimer | None" = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        StageTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        StageTimer.active = None
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        out = {}
+        for tag, a, b in self.records:
+            n, ms = out.get(tag, (0, 0.0))
+            out[tag] = (n + 1, ms + a.elapsed_time(b))
+        return out
+
+
+def _timed(tag: str, fn) -> None:
+    t = StageTimer.active
+    if t is None:
+        fn()
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    t.records.append((tag, a, b))
+
+
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -80,7 +117,7 @@ def project(hidden: torch.Tensor, weight: torch.Tensor, logits: torch.Tensor, ls
     a = _lib.ProjectArgs(hidden=hidden.data_ptr(), weight=weight.data_ptr(), logits=logits.data_ptr(),
                          lse_part=lse_part.data_ptr(), hidden_ld=hidden.stride(0), weight_ld=weight.stride(0),
                          logits_ld=logits.stride(0), n_rows=n, hidden_dim=h, vocab=v, cta_group=cta_group)
-    _lib.check(lib.clear_head_project(C.byref(a), _stream()), "clear_head_project")
+    _timed("gemm_project", lambda: _lib.check(lib.clear_head_project(C.byref(a), _stream()), "clear_head_project"))
 
 
 def rowloss(kind: int, logits: torch.Tensor, lse_part: torch.Tensor, loss_rows: torch.Tensor, vocab: int, *,
@@ -94,7 +131,7 @@ def rowloss(kind: int, logits: torch.Tensor, lse_part: torch.Tensor, loss_rows: 
                          scale_dev=_ptr(scale_dev), loss_rows=loss_rows.data_ptr(), logits_ld=logits.stride(0),
                          ref_ld=ref_logits.stride(0) if ref_logits is not None else 0, n_rows=logits.shape[0],
                          vocab=vocab, kind=kind, grad_scale=grad_scale, beta=beta, write_grad=int(write_grad))
-    _lib.check(lib.clear_head_rowloss(C.byref(a), _stream()), "clear_head_rowloss")
+    _timed("rowloss", lambda: _lib.check(lib.clear_head_rowloss(C.byref(a), _stream()), "clear_head_rowloss"))
 
 
 def backward(dlogits: torch.Tensor, vocab: int, hidden: torch.Tensor, weight: torch.Tensor,
@@ -109,7 +146,15 @@ def backward(dlogits: torch.Tensor, vocab: int, hidden: torch.Tensor, weight: to
                           hidden_dim=hidden.shape[1], vocab=vocab,
                           dweight_f32=int(dweight is not None and dweight.dtype == torch.float32),
                           accumulate=int(accumulate), cta_group=cta_group)
-    _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward")
+    if StageTimer.active is None or dhidden is None or dweight is None:
+        tag = "gemm_dweight" if dhidden is None else ("gemm_dhidden" if dweight is None else "gemm_backward")
+        _timed(tag, lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
+        return
+    # timed runs issue the two contractions separately so that each launch gets its own events
+    a.dweight = None
+    _timed("gemm_dhidden", lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
+    a.dweight, a.dhidden = dweight.data_ptr(), None
+    _timed("gemm_dweight", lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
 
 
 def count_valid(labels: torch.Tensor, inv_count: torch.Tensor) -> None:

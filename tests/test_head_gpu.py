@@ -1,0 +1,421 @@
+"""GPU parity tests of the fused loss head (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): loss rel <= 1e-3 (fp32 accumulation), bf16 gradients rel <= 2e-2
+(norm-wise per tensor; plus an element-wise bound of a few bf16 ulps of the tensor's max).
+The oracle is evaluated on the same bf16-rounded inputs and rounds logits to bf16 like a bf16
+checkpoint's lm_head does (straight-through), so that the comparison isolates the kernels' arithmetic.
+"""
+import math
+import types
+
+import pytest
+import torch
+
+from oracle import head_oracle as HO
+from tests._golden import MM_LOSSES, NLP_LOSSES, HeadCase
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-3
+GRAD_RTOL = 2e-2
+KINDS = [HO.KIND_CE, HO.KIND_KL_FWD, HO.KIND_KL_REV, HO.KIND_NPO, HO.KIND_ENTROPY]
+
+
+def _rel(got: torch.Tensor, want: torch.Tensor) -> float:
+    got, want = got.double().cpu(), want.double().cpu()
+    return ((got - want).norm() / want.norm().clamp_min(1e-30)).item()
+
+
+def _assert_grad(got, want, what):
+    got, want = got.double().cpu(), want.double().cpu()
+    assert torch.isfinite(got).all(), what
+    assert _rel(got, want) <= GRAD_RTOL, (what, _rel(got, want))
+    # element-wise: bf16 storage (2^-8 relative) plus accumulated rounding, relative to the tensor's scale
+    assert (got - want).abs().max().item() <= 3e-2 * want.abs().max().item() + 1e-12, what
+
+
+def _inputs(n, h, v, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    hid = torch.randn(n, h, generator=g).to(torch.bfloat16)
+    w = (0.05 * torch.randn(v, h, generator=g)).to(torch.bfloat16)
+    rh = (hid.float() + 0.3 * torch.randn(n, h, generator=g)).to(torch.bfloat16)
+    rw = (w.float() + 0.01 * torch.randn(v, h, generator=g)).to(torch.bfloat16)
+    y = torch.randint(0, v, (n,), generator=g)
+    y[::5] = -100
+    return hid, w, rh, rw, y
+
+
+def _oracle_fused(kind, hid, w, rh, rw, y, beta, coef, reduction="reference", n_seqs=None, row_weight=None):
+    """loss/dH/dW of one head invocation from the oracle's primitives, fp32 on the bf16-rounded inputs."""
+    h = hid.float().requires_grad_(True)
+    W = w.float().requires_grad_(True)
+    z = HO.project(h, W, torch.bfloat16)
+    zr = HO.project(rh.float(), rw.float(), torch.bfloat16).detach() if kind in (1, 2, 3) else None
+    n, v = z.shape
+    if reduction == "reference":
+        if kind == HO.KIND_CE:
+            loss = torch.nn.functional.cross_entropy(z, y, ignore_index=-100, reduction="mean")
+        elif kind == HO.KIND_KL_FWD:
+            loss = HO.kl_batchmean(HO.logits2probs(z), HO.logits2probs(zr))
+        elif kind == HO.KIND_KL_REV:
+            loss = HO.kl_batchmean(HO.logits2probs(zr), HO.logits2probs(z))
+        elif kind == HO.KIND_NPO:
+            loss = HO.npo_mm(z, zr, beta)
+        else:
+            loss = HO.neg_entropy_sum(z)
+    else:  # seq_mean over CE rows, optional row weights
+        rows = torch.nn.functional.cross_entropy(z, y, ignore_index=-100, reduction="none")
+        if row_weight is not None:
+            rows = rows * row_weight
+        loss = rows.sum() / n_seqs
+    loss = coef * loss
+    loss.backward()
+    return loss.detach(), h.grad, W.grad
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("v", [1000, 32000, 32064])
+def test_projection_and_lse(v):
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h = 200, 128
+    hid, w, *_ = _inputs(n, h, v, 1, dev)
+    hid, w = hid.to(dev), w.to(dev)
+    ld = (v + 63) // 64 * 64
+    z = torch.full((n, ld), 7.0, dtype=torch.bfloat16, device=dev)
+    part = torch.zeros(n, head.vtiles(v), 2, dtype=torch.float32, device=dev)
+    head.project(hid, w, z, part)
+    torch.cuda.synchronize()
+    ref = hid.float().cpu() @ w.float().cpu().t()
+    got = z[:, :v].float().cpu()
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    m = part[..., 0].max(dim=1, keepdim=True).values
+    lse = (m[:, 0] + torch.log((part[..., 1] * torch.exp(part[..., 0] - m)).sum(1))).cpu()
+    want = torch.logsumexp(got.double(), dim=-1)
+    assert (lse.double() - want).abs().max().item() <= 1e-4
+    # statistics of materialised logits (teacher handed over as a tensor) agree with the epilogue's
+    part2 = torch.zeros_like(part)
+    head._ref_lse(z, part2, v)
+    m2 = part2[..., 0].max(dim=1, keepdim=True).values
+    lse2 = (m2[:, 0] + torch.log((part2[..., 1] * torch.exp(part2[..., 0] - m2)).sum(1))).cpu()
+    assert (lse2.double() - want).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("v", [1000, 32064])
+def test_rowloss_vs_closed_forms(kind, v):
+    """clear_head_rowloss in isolation against SURVEY.md App. A closed forms (oracle.rowloss, fp64)."""
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h = 96, 128
+    beta = 0.7 if kind == HO.KIND_NPO else 1.0
+    hid, w, rh, rw, y = _inputs(n, h, v, 10 + kind, dev)
+    ld = (v + 63) // 64 * 64
+    nt = head.vtiles(v)
+    z = torch.zeros((n, ld), dtype=torch.bfloat16, device=dev)
+    zr = torch.zeros((n, ld), dtype=torch.bfloat16, device=dev)
+    part = torch.empty(n, nt, 2, dtype=torch.float32, device=dev)
+    rpart = torch.empty(n, nt, 2, dtype=torch.float32, device=dev)
+    head.project(hid.to(dev), w.to(dev), z, part)
+    head.project(rh.to(dev), rw.to(dev), zr, rpart)
+    z64, zr64 = z[:, :v].double().cpu(), zr[:, :v].double().cpu()
+    want_rows, want_d = HO.rowloss(kind, z64, zr64, y, beta)
+    rows = torch.empty(n, dtype=torch.float32, device=dev)
+    needs_ref = kind in (1, 2, 3)
+    # forward only leaves the logits untouched
+    before = z.clone()
+    head.rowloss(kind, z, part, rows, v, ref_logits=zr if needs_ref else None, ref_lse_part=rpart if needs_ref else None,
+                 labels=y.to(dev) if kind == 0 else None, beta=beta, write_grad=False)
+    assert torch.equal(before, z)
+    assert (rows.double().cpu() - want_rows).abs().max().item() <= LOSS_RTOL * want_rows.abs().max().item()
+    head.rowloss(kind, z, part, rows, v, ref_logits=zr if needs_ref else None, ref_lse_part=rpart if needs_ref else None,
+                 labels=y.to(dev) if kind == 0 else None, beta=beta, grad_scale=0.5, write_grad=True)
+    torch.cuda.synchronize()
+    assert (rows.double().cpu() - want_rows).abs().max().item() <= LOSS_RTOL * want_rows.abs().max().item()
+    _assert_grad(z[:, :v], 0.5 * want_d, f"dlogits kind {kind}")
+    assert (z[:, v:] == 0).all(), "padding columns must be zeroed"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("shape", [(300, 136, 1000), (512, 128, 32000), (130, 256, 32064)])
+def test_fused_head_vs_oracle(kind, shape):
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h, v = shape
+    beta = 0.7 if kind == HO.KIND_NPO else 1.0
+    coef = -0.7
+    hid, w, rh, rw, y = _inputs(n, h, v, 20 + kind, dev)
+    want_loss, want_dh, want_dw = _oracle_fused(kind, hid, w, rh, rw, y, beta, coef)
+    for block_rows in (None, 128):
+        res = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), kind, labels=y.to(dev), ref_hidden=rh.to(dev),
+                                     ref_weight=rw.to(dev), beta=beta, coef=coef, block_rows=block_rows)
+        torch.cuda.synchronize()
+        assert abs(res.loss.item() - want_loss.item()) <= LOSS_RTOL * abs(want_loss.item()), (res.loss.item(), want_loss.item())
+        _assert_grad(res.dhidden, want_dh, f"dH kind {kind} block {block_rows}")
+        _assert_grad(res.dweight, want_dw, f"dW kind {kind} block {block_rows}")
+        assert res.dweight.dtype == torch.bfloat16 and res.dhidden.dtype == torch.bfloat16
+
+
+def test_teacher_as_materialised_logits():
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h, v = 256, 128, 1000
+    hid, w, rh, rw, y = _inputs(n, h, v, 31, dev)
+    a = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_KL_FWD, ref_hidden=rh.to(dev), ref_weight=rw.to(dev))
+    zr = (rh.to(dev).float() @ rw.to(dev).float().t()).to(torch.bfloat16)
+    b = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_KL_FWD, ref_logits=zr.contiguous())
+    assert abs(a.loss.item() - b.loss.item()) <= 1e-3 * abs(a.loss.item())
+    assert _rel(b.dweight, a.dweight) < 1e-2
+
+
+def test_dweight_accumulates_in_fp32_across_calls():
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h, v = 256, 128, 1000
+    hid, w, rh, rw, y = _inputs(n, h, v, 32, dev)
+    acc = torch.zeros(v, h, dtype=torch.float32, device=dev)
+    one = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, labels=y.to(dev))
+    for _ in range(2):
+        head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, labels=y.to(dev), dweight_accum=acc, block_rows=128)
+    assert _rel(acc, 2 * one.dweight.float()) < 1e-2
+
+
+def test_seq_mean_and_row_weights():
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    b, t, h, v = 4, 40, 128, 1000
+    hid, w, rh, rw, y = _inputs(b * t, h, v, 33, dev)
+    rwt = torch.rand(b).repeat_interleave(t)
+    want_loss, want_dh, want_dw = _oracle_fused(0, hid, w, rh, rw, y, 1.0, -1.0, "seq_mean", b, rwt)
+    res = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, labels=y.to(dev), coef=-1.0, reduction="seq_mean",
+                                 n_seqs=b, row_weight=rwt.to(dev))
+    assert abs(res.loss.item() - want_loss.item()) <= LOSS_RTOL * abs(want_loss.item())
+    _assert_grad(res.dhidden, want_dh, "dH seq_mean")
+    _assert_grad(res.dweight, want_dw, "dW seq_mean")
+    # forward-only per-sequence sums == get_batch_loss
+    z = HO.project(hid.float(), w.float(), torch.bfloat16).view(b, t, v)
+    labels = torch.cat([torch.full((b, 1), -100), y.view(b, t)[:, :-1]], dim=1)  # unshifted labels whose shift is y
+    want = HO.get_batch_loss(z, labels)
+    # get_batch_loss drops the last row; y's last column must then be ignored for equality
+    y2 = y.view(b, t).clone()
+    y2[:, -1] = -100
+    seq = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, labels=y2.reshape(-1).to(dev), reduction="seq_mean",
+                                 n_seqs=b, need_dhidden=False, need_dweight=False).seq_loss
+    assert (seq.cpu() - want).abs().max().item() <= LOSS_RTOL * want.abs().max().item()
+
+
+def test_edge_cases():
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h, v = 64, 128, 1000
+    hid, w, rh, rw, y = _inputs(n, h, v, 34, dev)
+    # all rows ignored: HF's mean CE is NaN (0/0); gradients are zero rows times inf -> the reference gives NaN too
+    res = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, labels=torch.full((n,), -100, device=dev))
+    assert math.isnan(res.loss.item())
+    # one single valid row
+    y1 = torch.full((n,), -100)
+    y1[17] = 3
+    want_loss, want_dh, want_dw = _oracle_fused(0, hid, w, rh, rw, y1, 1.0, 1.0)
+    res = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, labels=y1.to(dev))
+    assert abs(res.loss.item() - want_loss.item()) <= LOSS_RTOL * abs(want_loss.item())
+    assert (res.dhidden[:17] == 0).all() and (res.dhidden[18:] == 0).all()
+    _assert_grad(res.dhidden, want_dh, "dH single row")
+    # a single row, tiny vocab
+    res = head.head_loss_fwd_bwd(hid[:1].to(dev), w[:13].contiguous().to(dev), HO.KIND_ENTROPY)
+    want_loss, _, _ = _oracle_fused(4, hid[:1], w[:13], rh[:1], rw[:13], y[:1], 1.0, 1.0)
+    assert abs(res.loss.item() - want_loss.item()) <= LOSS_RTOL * abs(want_loss.item())
+    # errors: no silent fallback
+    with pytest.raises(RuntimeError):
+        head.head_loss_fwd_bwd(hid, w, HO.KIND_CE, labels=y)  # CPU tensors
+    with pytest.raises(RuntimeError):
+        head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_NPO)  # teacher missing
+    with pytest.raises(RuntimeError):
+        head.head_loss_fwd_bwd(hid.to(dev).float(), w.to(dev), HO.KIND_CE, labels=y.to(dev))  # dtype
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's own outputs (tests/golden, produced by oracle/gen_golden.py) through the recipes
+# --------------------------------------------------------------------------------------------------
+def _run_recipe(case: HeadCase, dev):
+    from multimodal_unlearning_b200 import trainer as T
+    hid = {n: h.to(dev).to(torch.bfloat16).requires_grad_(True) for n, h in zip(case.student_splits, case.hidden)}
+    lab = {n: y.to(dev) for n, y in zip(case.student_splits, case.labels)}
+    ref = {n: h.to(dev).to(torch.bfloat16) for n, h in zip(case.teacher_splits, case.ref_hidden)}
+    w = case.weight.to(dev).to(torch.bfloat16).requires_grad_(True)
+    wr = case.ref_weight.to(dev).to(torch.bfloat16)
+
+    class FakeModel(torch.nn.Module):
+        """Trunk stand-in: returns the recorded hidden states of the split whose input_ids tag it carries."""
+
+        def __init__(self, table, weight):
+            super().__init__()
+            self.table = table
+            self.lm_head = torch.nn.Linear(weight.shape[1], weight.shape[0], bias=False, device=dev, dtype=torch.bfloat16)
+            self.lm_head.weight = torch.nn.Parameter(weight.detach().clone())
+            self.config = types.SimpleNamespace(image_token_index=None)
+
+        def get_output_embeddings(self):
+            return self.lm_head
+
+        def forward(self, input_ids=None, attention_mask=None, **kw):
+            name = self.names[int(input_ids.flatten()[0])]
+            return types.SimpleNamespace(logits=self.lm_head(self.table[name]))
+
+    names = sorted(set(case.student_splits) | set(case.teacher_splits))
+    student = FakeModel(hid, w)
+    student.names = names
+    teacher = FakeModel(ref, wr)
+    teacher.names = names
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+
+    def tag(name, like):
+        return torch.full_like(like, names.index(name))
+
+    if case.trainer == "mm":
+        inputs = {}
+        rnd = [n for n in case.student_splits if n.startswith("random")]
+        for n in names:
+            if n.startswith("random"):
+                continue
+            y = lab.get(n, torch.zeros(2, case.hidden[0].shape[1], dtype=torch.int64, device=dev))
+            inputs[n] = {"input_ids": tag(n, y), "attention_mask": torch.ones_like(y), "labels": y}
+        if "retain" not in inputs:  # the reference always moves inputs["retain"] to the device
+            y = next(iter(lab.values()))
+            inputs["retain"] = {"input_ids": tag(names[0], y), "attention_mask": torch.ones_like(y), "labels": y}
+        if rnd:
+            ys = torch.stack([lab[n] for n in rnd], dim=1)  # [B, K, L]
+            ids = torch.stack([tag(n, lab[n]) for n in rnd], dim=1)
+            inputs["random"] = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": ys}
+        fake = types.SimpleNamespace(loss_type=case.loss_type.lower(), teacher_model=teacher, loss_beta=case.beta,
+                                     l1_lambda=0.0, l0_lambda=0.0, l_norm_from="zero",
+                                     loss_args={"bad_weight": 2.5, "random_weight": 1.0, "normal_weight": 0.5})
+        loss = T.MMTrainerForgetting.compute_loss(fake, student, inputs)
+    else:
+        def triple(n):
+            y = lab[n]
+            return (tag(n, y), y, torch.ones_like(y))
+        if case.loss_type == "idk":
+            # one forward over cat(forget, retain): the fixture holds it as a single 4-sequence split
+            y = lab["forget+retain"]
+            half = y.shape[0] // 2
+            student.table["forget+retain"] = hid["forget+retain"]
+            f = (tag("forget+retain", y[:half]), y[:half], torch.ones_like(y[:half]))
+            r = (tag("forget+retain", y[half:]), y[half:], torch.ones_like(y[half:]))
+            inputs = [f, r]
+        else:
+            first = case.student_splits[0]
+            inputs = [triple("forget") if "forget" in lab else triple(first),
+                      triple("retain") if "retain" in lab else triple(first)]
+            if "idk" in lab:
+                inputs.append(triple("idk"))
+        fake = types.SimpleNamespace(loss_type=case.loss_type, oracle_model=teacher, loss_beta=case.beta, l1_lambda=0.0,
+                                     l0_lambda=0.0)
+        loss = T.CustomTrainerForgetting.compute_loss(fake, student, inputs)
+    loss.backward()
+    return loss, hid, student.lm_head.weight.grad
+
+
+def _oracle_on_bf16(case: HeadCase):
+    student, teacher, w, wr = case.oracle_inputs(cast=torch.bfloat16)
+    fn = HO.mm_compute_loss if case.trainer == "mm" else HO.nlp_compute_loss
+    if case.trainer == "nlp" and case.loss_type == "npo":
+        fn = HO.mm_compute_loss  # App. B #3: the nlp formula is NaN by construction; the product evaluates the mm one
+    return HO.loss_and_grads(fn, student, w, teacher=teacher, ref_weight=wr, beta=case.beta, loss_type=case.loss_type,
+                             logits_dtype=torch.bfloat16)
+
+
+@pytest.mark.parametrize("trainer,loss_type", [("mm", l) for l in MM_LOSSES] + [("nlp", l) for l in NLP_LOSSES])
+def test_recipes_against_reference_fixtures(trainer, loss_type):
+    case = HeadCase(trainer, loss_type)
+    dev = torch.device("cuda:0")
+    loss, hid, dw = _run_recipe(case, dev)
+    want_loss, want_dh, want_dw = _oracle_on_bf16(case)
+    assert abs(loss.item() - want_loss.item()) <= LOSS_RTOL * max(abs(want_loss.item()), 1e-3), (loss.item(), want_loss.item())
+    for n in case.student_splits:
+        key = n
+        if n.startswith("random"):
+            key = n
+        want = want_dh.get(key)
+        got = hid[n].grad
+        if want is None or want.abs().max() == 0:
+            assert got is None or got.abs().max().item() == 0
+            continue
+        _assert_grad(got.reshape(want.shape), want, f"{loss_type} dH[{n}]")
+    _assert_grad(dw, want_dw, f"{loss_type} dW")
+    # and against what the reference itself returned in fp32 on the unrounded inputs (looser: bf16 inputs)
+    if not math.isnan(case.loss):
+        assert abs(loss.item() - case.loss) <= 2e-2 * max(abs(case.loss), 1.0), (loss.item(), case.loss)
+        got_rows = dw[case.probe_rows.to(dev)].float().cpu()
+        assert _rel(got_rows, case.dw_rows) <= 6e-2
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: full-size checks against a chunked fp32 torch restatement on the GPU + properties
+# --------------------------------------------------------------------------------------------------
+def _torch_reference_fullsize(kind, hid, w, rh, rw, y, beta, chunk=1024):
+    n, h = hid.shape
+    v = w.shape[0]
+    dH = torch.empty(n, h, dtype=torch.float32, device=hid.device)
+    dW = torch.zeros(v, h, dtype=torch.float32, device=hid.device)
+    wf, rwf = w.float(), rw.float()
+    total = torch.zeros((), dtype=torch.float64, device=hid.device)
+    m = (y != -100).sum()
+    for r0 in range(0, n, chunk):
+        hb = hid[r0:r0 + chunk].float()
+        z = (hb @ wf.t()).to(torch.bfloat16).float()
+        lp = torch.log_softmax(z, -1)
+        p = lp.exp()
+        if kind == HO.KIND_CE:
+            yy = y[r0:r0 + chunk]
+            valid = (yy != -100)
+            rows = -lp.gather(1, yy.clamp(min=0)[:, None])[:, 0] * valid
+            d = p.clone()
+            d[torch.arange(d.shape[0], device=d.device), yy.clamp(min=0)] -= 1
+            d = d * valid[:, None] / m
+            total += rows.double().sum() / m
+        else:  # NPO
+            zr = (rh[r0:r0 + chunk].float() @ rwf.t()).to(torch.bfloat16).float()
+            q = torch.softmax(zr, -1)
+            t = (p / (q + 1e-8)).pow(beta)
+            s = t / (1 + t)
+            total += torch.log1p(t).double().sum() * (2.0 / (beta * n * v))
+            d = (s - p * s.sum(-1, keepdim=True)) * (2.0 / (n * v))
+        dH[r0:r0 + chunk] = d @ wf
+        dW += d.t() @ hb
+    return total, dH, dW
+
+
+@pytest.mark.parametrize("kind,n,h,v", [(HO.KIND_NPO, 8192, 4096, 32064), (HO.KIND_CE, 8192, 4096, 32000)])
+def test_baseline_size_parity(kind, n, h, v):
+    """BASELINE.json configs[1] (NPO, bs 8 x seq 1024, LLaVA-1.5-7B head) and configs[4] (grad_ascent, bs 16 x 512)."""
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    hid = torch.randn(n, h, generator=g, device=dev).to(torch.bfloat16)
+    w = (0.02 * torch.randn(v, h, generator=g, device=dev)).to(torch.bfloat16)
+    rh = (hid.float() + 0.05 * torch.randn(n, h, generator=g, device=dev)).to(torch.bfloat16)
+    rw = w
+    y = torch.randint(0, v, (n,), generator=g, device=dev)
+    y[1023::1024] = -100
+    res = head.head_loss_fwd_bwd(hid, w, kind, labels=y, ref_hidden=rh, ref_weight=rw, beta=1.0)
+    want_loss, want_dh, want_dw = _torch_reference_fullsize(kind, hid, w, rh, rw, y, 1.0)
+    assert abs(res.loss.item() - want_loss.item()) <= LOSS_RTOL * abs(want_loss.item()), (res.loss.item(), want_loss.item())
+    assert _rel(res.dhidden, want_dh) <= GRAD_RTOL
+    assert _rel(res.dweight, want_dw) <= GRAD_RTOL
+    # size-independent properties: rows of a softmax-type gradient sum to zero, so dW's column sums vanish
+    # and dH is orthogonal to nothing in particular but must be finite; ignored CE rows give exactly zero dH.
+    col = res.dweight.float().sum(0)
+    assert col.abs().max().item() <= 2e-2 * res.dweight.float().abs().sum(0).max().item()
+    if kind == HO.KIND_CE:
+        assert (res.dhidden[1023::1024] == 0).all()
+    # the oracle proper (CPU) on a row subset: loss rows and dH rows only need those rows
+    idx = torch.tensor([0, 1, 511, 4095, 8191])
+    z = HO.project(hid[idx.to(dev)].float().cpu(), w.float().cpu(), torch.bfloat16)
+    zr = HO.project(rh[idx.to(dev)].float().cpu(), rw.float().cpu(), torch.bfloat16)
+    rows, dterm = HO.rowloss(kind, z.double(), zr.double(), y[idx.to(dev)].cpu(), 1.0)
+    got_rows = res.loss_rows[idx.to(dev)].double().cpu()
+    assert (got_rows - rows).abs().max().item() <= LOSS_RTOL * rows.abs().max().item()
+    scale = (1.0 / (y != -100).sum().item()) if kind == HO.KIND_CE else 2.0 / (n * v)
+    want_rows_dh = (dterm * scale) @ w.double().cpu()
+    assert _rel(res.dhidden[idx.to(dev)], want_rows_dh) <= GRAD_RTOL

@@ -1,0 +1,178 @@
+"""GPU parity tests of the SalUn saliency mask and the masked AdamW step (through the C ABI).
+Integer / byte results (accumulated bf16 bit patterns, thresholds, int8 masks) must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import salun_oracle as SO
+from tests._golden import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _flat(layout, named: dict, dtype):
+    buf = torch.zeros(layout.total, dtype=dtype)
+    for i, n in enumerate(layout.names):
+        buf[layout.offsets[i]: layout.offsets[i] + layout.numels[i]] = named[n].reshape(-1)
+    return buf
+
+
+def _check_masks(state, named_acc, thresholds):
+    want = SO.masks(named_acc, thresholds)
+    got = dict(state.masks(thresholds))
+    for th in thresholds:
+        for n in named_acc:
+            g = got[th][n].cpu().numpy()
+            assert g.dtype == np.int8 and g.shape == tuple(named_acc[n].shape)
+            assert np.array_equal(g, want[th][n]), (th, n, int((g != want[th][n]).sum()))
+
+
+def test_reference_fixture_bit_exact():
+    """Per-batch gradients recorded from the reference's save_gradient_ratio -> same ten masks."""
+    from multimodal_unlearning_b200 import salun
+    z = np.load(GOLDEN / "salun_tiny.npz")
+    names = [str(n) for n in z["names"]]
+    shapes = [tuple(int(x) for x in str(s).split(";")) for s in z["shapes"]]
+    layout = salun.FlatLayout(list(zip(names, shapes)))
+    offs = np.concatenate([[0], np.cumsum(layout.numels)])
+    state = salun.SaliencyState(layout, "cuda:0")
+    acc = None
+    for b in range(3):
+        g = torch.from_numpy(z[f"grad_{b}"].copy()).view(torch.bfloat16)
+        named = {n: g[offs[i]:offs[i + 1]] for i, n in enumerate(names)}
+        state.accumulate_flat(_flat(layout, named, torch.bfloat16).cuda())
+        acc = g.clone() if acc is None else SO.accumulate(acc, g)
+    named_acc = {n: acc[offs[i]:offs[i + 1]].reshape(shapes[i]) for i, n in enumerate(names)}
+    got_acc = state.acc.cpu()
+    for i, n in enumerate(names):
+        a = got_acc[layout.offsets[i]: layout.offsets[i] + layout.numels[i]]
+        assert torch.equal(a.view(torch.int16), named_acc[n].reshape(-1).view(torch.int16)), n
+    n_total = int(offs[-1])
+    for th, hard in state.masks(SO.REFERENCE_THRESHOLDS):
+        flat = np.concatenate([hard[n].reshape(-1).cpu().numpy() for n in names])
+        stable = np.unpackbits(z[f"mask_stable_{th}"])[:n_total].astype(np.int8)
+        assert np.array_equal(flat, stable), th
+
+
+def test_ties_odd_sizes_and_special_values():
+    from multimodal_unlearning_b200 import salun
+    g = torch.Generator().manual_seed(0)
+    shapes = {"a": (1000003,), "b": (8,), "c": (3, 5), "d": (2048, 1024), "e": (1,), "f": (70000,)}
+    named = {}
+    for n, s in shapes.items():
+        x = torch.randn(*s, generator=g)
+        named[n] = x
+    named["a"] = (named["a"] * 4).round() / 4            # heavy ties
+    named["d"][:, ::3] = 0.0                              # a third exact zeros
+    named["d"][5, 7] = 1e6                                # overflows fp16 -> inf
+    named["d"][6, 7] = -7e4
+    named["f"] = named["f"] * 1e-9                        # flushes to fp16 zero / subnormals
+    named = {n: v.to(torch.bfloat16) for n, v in named.items()}
+    layout = salun.FlatLayout([(n, v.shape) for n, v in named.items()])
+    state = salun.SaliencyState(layout, "cuda:0")
+    state.accumulate_flat(_flat(layout, named, torch.bfloat16).cuda())
+    ths = (0.0, 0.1, 0.25, 0.5, 0.9, 0.999, 1.0)
+    _check_masks(state, named, ths)
+    sel = state.select(ths).cpu().numpy()
+    for i, n in enumerate(layout.names):
+        keys = SO.saliency_keys(named[n])
+        for j, th in enumerate(ths):
+            assert tuple(sel[i, j]) == SO.select(keys, th), (n, th)
+
+
+def test_accumulate_per_tensor_matches_flat():
+    from multimodal_unlearning_b200 import salun
+    model = torch.nn.Sequential(torch.nn.Linear(64, 48), torch.nn.Linear(48, 10)).to(torch.bfloat16).cuda()
+    layout = salun.FlatLayout.of_model(model)
+    state = salun.SaliencyState(layout, "cuda:0")
+    acc = {n: None for n in layout.names}
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        for n, p in model.named_parameters():
+            p.grad = torch.randn(p.shape, generator=g).to(torch.bfloat16).cuda()
+            gr = p.grad.cpu()
+            acc[n] = gr.clone() if acc[n] is None else SO.accumulate(acc[n], gr)
+        state.accumulate_model(model)
+    for i, n in enumerate(layout.names):
+        assert torch.equal(layout.view(state.acc, i).cpu().view(torch.int16), acc[n].view(torch.int16))
+    _check_masks(state, acc, (0.3, 0.5))
+
+
+def test_large_properties():
+    """Sizes far beyond what the CPU sort finishes in seconds: order-statistic properties instead."""
+    from multimodal_unlearning_b200 import salun
+    dev = torch.device("cuda:0")
+    shapes = [("w0", (4096, 11008)), ("w1", (32000, 4096)), ("n0", (4096,)), ("w2", (11008, 4096))]
+    layout = salun.FlatLayout(shapes)
+    state = salun.SaliencyState(layout, dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    grads = (1e-3 * torch.randn(layout.total, generator=g, device=dev)).to(torch.bfloat16)
+    state.accumulate_flat(grads)
+    assert torch.equal(state.acc, grads)
+    ths = (0.1, 0.5, 0.9, 1.0)
+    sel = state.select(ths)
+    prev = None
+    keys_all = state.acc.float().abs().to(torch.float16).view(torch.int16).to(torch.int32)
+    for j, th in enumerate(ths):
+        flat = state.mask_flat(sel, j)
+        for i, (n, s) in enumerate(shapes):
+            m = layout.view(flat, i).reshape(-1)
+            k = layout.view(keys_all, i).reshape(-1)
+            cnt = int(m.sum().item())
+            assert cnt == int(th * m.numel()), (n, th)                      # exactly k ones
+            if 0 < cnt < m.numel():
+                lo_sel = k[m == 1].min().item()
+                hi_unsel = k[m == 0].max().item()
+                assert lo_sel >= hi_unsel                                   # a top-k set
+                tau = int(sel[i, j, 0].item())
+                assert lo_sel == tau
+                # ties: selected tau-elements come before unselected ones (stable order)
+                tie = (k == tau)
+                pos = torch.nonzero(tie).reshape(-1)
+                picked = m[pos]
+                assert (picked[:-1] >= picked[1:]).all()
+        if prev is not None:
+            assert ((prev == 1) & (flat == 0)).sum().item() == 0            # nested across thresholds
+        prev = flat
+
+
+def test_masked_adamw_bit_exact():
+    from multimodal_unlearning_b200 import salun
+    dev = torch.device("cuda:0")
+    n = 1_000_003  # not a multiple of 8: exercises the tail
+    g = torch.Generator().manual_seed(3)
+    p = torch.randn(n, generator=g).to(torch.bfloat16)
+    mask = (torch.rand(n, generator=g) < 0.5).to(torch.int8)
+    m = np.zeros(n, np.float32)
+    v = np.zeros(n, np.float32)
+    pd = p.clone().to(dev)
+    md = torch.zeros(n, dtype=torch.float32, device=dev)
+    vd = torch.zeros(n, dtype=torch.float32, device=dev)
+    for step in (1, 2, 3):
+        grad = (0.01 * torch.randn(n, generator=g)).to(torch.bfloat16)
+        p, m, v = SO.adamw_step(p, grad, m, v, mask.numpy(), step, lr=1e-3, weight_decay=0.01)
+        salun.masked_adamw_flat(pd, grad.to(dev), md, vd, mask.to(dev), step, lr=1e-3, weight_decay=0.01)
+        assert torch.equal(pd.cpu().view(torch.int16), p.view(torch.int16)), step
+        assert np.array_equal(md.cpu().numpy().view(np.int32), m.view(np.int32)), step
+        assert np.array_equal(vd.cpu().numpy().view(np.int32), v.view(np.int32)), step
+
+
+def test_masked_adamw_optimizer_matches_torch_adamw_when_mask_is_ones():
+    from multimodal_unlearning_b200 import salun
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    w = torch.randn(256, 128, device=dev).to(torch.bfloat16)
+    p1 = torch.nn.Parameter(w.clone())
+    p2 = torch.nn.Parameter(w.float().clone())
+    o1 = salun.MaskedAdamW([p1], lr=1e-3, weight_decay=0.01)
+    o2 = torch.optim.AdamW([p2], lr=1e-3, weight_decay=0.01, foreach=False)
+    o1.set_mask(p1, torch.ones_like(w, dtype=torch.int8))
+    for _ in range(3):
+        g = (0.01 * torch.randn(256, 128, device=dev)).to(torch.bfloat16)
+        p1.grad = g.clone()
+        p2.grad = g.float()
+        o1.step()
+        o2.step()
+        p2.data = p2.data.to(torch.bfloat16).float()  # our parameters are stored in bf16 after every step
+    assert (p1.float() - p2).abs().max().item() <= 2 ** -7 * p2.abs().max().item()
+    assert torch.allclose(o1.state[p1]["exp_avg"], o2.state[p2]["exp_avg"], rtol=1e-5, atol=1e-9)
