@@ -152,11 +152,12 @@ __global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossPa
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
   const int nvec = (int)(a.ld >> 3);
+  const int ref_nvec = (int)(a.ref_ld >> 3);  // a materialised teacher may be narrower than the staging buffer
   float acc = 0.f;
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-    unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
     const int c0 = v << 3;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -235,11 +236,12 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
   const int nvec = (int)(a.ld >> 3);
+  const int ref_nvec = kNeedsRef ? (int)(a.ref_ld >> 3) : 0;
   float stat = 0.f, loss = 0.f;
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-    if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
     const int c0 = v << 3;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-    if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
     const int c0 = v << 3;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -377,7 +379,8 @@ int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
   const bool needs_ref = a->kind == CLEAR_KIND_KL_FWD || a->kind == CLEAR_KIND_KL_REV || a->kind == CLEAR_KIND_NPO;
   if (needs_ref) {
     if (!a->ref_logits || !a->ref_lse_part) return fail(CLEAR_ERR_NULL, "clear_head_rowloss: kind %d needs teacher logits", a->kind);
-    if (a->ref_ld < a->logits_ld || a->ref_ld % 8) return fail(CLEAR_ERR_SHAPE, "clear_head_rowloss: bad ref_ld");
+    if (a->ref_ld < a->vocab || a->ref_ld % 8) return fail(CLEAR_ERR_SHAPE, "clear_head_rowloss: ref_ld must be >= vocab and a multiple of 8");
+    if (reinterpret_cast<uintptr_t>(a->ref_logits) & 15) return fail(CLEAR_ERR_ALIGN, "clear_head_rowloss: ref_logits must be 16-byte aligned");
   }
   if (a->kind == CLEAR_KIND_CE && !a->labels) return fail(CLEAR_ERR_NULL, "clear_head_rowloss: CE needs labels");
   if (a->kind == CLEAR_KIND_NPO && !(a->beta > 0.f)) return fail(CLEAR_ERR_SHAPE, "clear_head_rowloss: NPO beta must be > 0");
