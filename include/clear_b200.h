@@ -179,7 +179,9 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
                              uint32_t* hist, void* stream);
 /* For each segment and each of n_th thresholds: k = (int64)(th * numel) (double product truncated,
  * as Python int()); finds tau = bit pattern of the k-th largest value and the number of ties to
- * take.  select: int64 [n_segs][n_th][2] = (tau_bits or -1 when k == 0, ties_to_take).
+ * take.  select: int64 [n_segs][n_th][5] = (tau_bits or -1 when k == 0, ties_to_take, lo, hi, total) with
+ * [lo, hi] the bf16 magnitude bit patterns whose key is tau and total = #{key == tau} in the tensor
+ * (both used by the mask pass).
  * seg_numel_dev: optional device int64 [n_segs] true element counts for tensors stored zero-padded
  * to the next multiple of 8 (NULL: numel = offset difference).  thresholds: host doubles. */
 int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, const int64_t* seg_numel_dev,
@@ -189,11 +191,13 @@ int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, 
  * th_index selects which threshold's (tau, ties) of `select` to use.
  * Work is cut into chunks of clear_saliency_chunk_elems() elements that never straddle tensors:
  * chunk_prefix_dev: device int64 [n_segs+1], chunk_prefix[s] = sum_{t<s} ceil(numel_t / chunk);
- * n_chunks = chunk_prefix[n_segs]; tie_scratch: uint32 [n_chunks] workspace. */
+ * n_chunks = chunk_prefix[n_segs]; tie_scratch: uint64 [n_chunks] workspace.
+ * One streaming pass writes the mask speculating on the tie boundary from the histogram; a scan of the
+ * chunk tie counts and an audit pass rewrite the few chunks that guessed wrong (result is exact). */
 int64_t clear_saliency_chunk_elems(void);
 int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
                         int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
-                        uint32_t* tie_scratch, int8_t* mask, void* stream);
+                        uint64_t* tie_scratch, int8_t* mask, void* stream);
 /* Masked AdamW: g' = g * mask; torch _single_tensor_adam op order, fp32 states.
  * param, grad bf16; exp_avg, exp_avg_sq fp32; mask int8 (NULL = all ones). step >= 1. */
 typedef struct ClearAdamWArgs {

@@ -83,10 +83,19 @@ __device__ __forceinline__ int find_segment(const int64_t* off, int n_segs, int6
   return lo;
 }
 
-__global__ void __launch_bounds__(512) histogram_kernel(const __nv_bfloat16* acc, const int64_t* seg_off, int n_segs,
-                                                        int64_t n_total, int64_t per_block, uint32_t* hist) {
+// bf16 sums have 8 significant bits, so their fp16 keys are multiples of 8: taken as they are, the
+// populated bins of the shared histogram would all live in 4 of the 32 banks.  The low 3 bits are
+// rotated to the top of the shared-memory index, which makes the populated bins contiguous.
+__device__ __forceinline__ uint32_t bin_slot(uint32_t key) { return (key >> 3) | ((key & 7u) << 12); }
+__device__ __forceinline__ uint32_t slot_bin(uint32_t slot) { return ((slot & 0xFFFu) << 3) | (slot >> 12); }
+
+constexpr int kHistThreads = 1024;
+constexpr int kHistUnroll = 4;  // 128-bit loads in flight per thread
+
+__global__ void __launch_bounds__(kHistThreads) histogram_kernel(const __nv_bfloat16* acc, const int64_t* seg_off, int n_segs,
+                                                                 int64_t n_total, int64_t per_block, uint32_t* hist) {
   extern __shared__ uint32_t sh[];
-  for (int b = threadIdx.x; b < kBins; b += blockDim.x) sh[b] = 0;
+  for (int b = threadIdx.x; b < kBins; b += kHistThreads) sh[b] = 0;
   __syncthreads();
   int64_t pos = (int64_t)blockIdx.x * per_block;
   const int64_t end = min(pos + per_block, n_total);
@@ -96,18 +105,29 @@ __global__ void __launch_bounds__(512) histogram_kernel(const __nv_bfloat16* acc
     while (seg_off[seg + 1] <= pos) ++seg;  // skips empty tensors
     const int64_t stop = min(end, seg_off[seg + 1]);
     const int64_t v1 = stop >> 3;
-    for (int64_t v = (pos >> 3) + threadIdx.x; v < v1; v += blockDim.x) {
-      const uint4 raw = ld_stream(reinterpret_cast<const uint4*>(acc) + v);
-      uint32_t k[8];
-      keys8(raw, k);
+    for (int64_t v0 = (pos >> 3) + threadIdx.x; v0 < v1; v0 += (int64_t)kHistThreads * kHistUnroll) {
+      uint4 raw[kHistUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sh[k[j]], 1u);
+      for (int u = 0; u < kHistUnroll; ++u) {
+        const int64_t v = v0 + (int64_t)u * kHistThreads;
+        if (v < v1) raw[u] = ld_stream(reinterpret_cast<const uint4*>(acc) + v);
+      }
+#pragma unroll
+      for (int u = 0; u < kHistUnroll; ++u) {
+        const int64_t v = v0 + (int64_t)u * kHistThreads;
+        if (v < v1) {
+          uint32_t k[8];
+          keys8(raw[u], k);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(&sh[bin_slot(k[j])], 1u);
+        }
+      }
     }
     __syncthreads();
     uint32_t* out = hist + (size_t)seg * kBins;
-    for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
+    for (int b = threadIdx.x; b < kBins; b += kHistThreads) {
       const uint32_t c = sh[b];
-      if (c) { atomicAdd(&out[b], c); sh[b] = 0; }
+      if (c) { atomicAdd(&out[slot_bin(b)], c); sh[b] = 0; }
     }
     __syncthreads();
     pos = stop;
@@ -117,7 +137,36 @@ __global__ void __launch_bounds__(512) histogram_kernel(const __nv_bfloat16* acc
 // ------------------------------------------------------------------------------------------------
 // Select: one CTA per tensor.  Descending cumulative counts over the bins; for every threshold the bin
 // tau with  #{key > tau} < k <= #{key >= tau}  and ties = k - #{key > tau}.
+// Output per (tensor, threshold): (tau, ties, lo, hi, total) where total = #{key == tau} and [lo, hi] is the range of bf16 magnitude bit
+// patterns whose key equals tau (the key is monotone in the magnitude pattern), so that the mask pass
+// compares raw 16-bit patterns and never converts:  key > tau  <=>  |x|bits > hi.
 // ------------------------------------------------------------------------------------------------
+constexpr int kSelFields = 5;
+__device__ __forceinline__ uint32_t key_of_pattern(uint32_t m) {
+  return sal_key(__ushort_as_bfloat16((unsigned short)m));
+}
+__device__ void write_select(int64_t* out, int64_t tau, int64_t ties, int64_t total) {
+  out[0] = tau;
+  out[1] = ties;
+  out[4] = total;  // elements of the tensor whose key is tau
+  if (tau < 0) {  // nothing selected: no pattern is above hi, none inside [lo, hi]
+    out[2] = 0x8000;
+    out[3] = 0x7FFF;
+    return;
+  }
+  uint32_t lo = 0, hi = 0x7FFF;  // smallest m with key(m) >= tau
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (key_of_pattern(mid) >= (uint32_t)tau) hi = mid; else lo = mid + 1;
+  }
+  out[2] = lo;
+  uint32_t a = lo, b = 0x7FFF;   // largest m with key(m) <= tau
+  while (a < b) {
+    const uint32_t mid = (a + b + 1) >> 1;
+    if (key_of_pattern(mid) <= (uint32_t)tau) a = mid; else b = mid - 1;
+  }
+  out[3] = a;
+}
 constexpr int kMaxThresholds = 16;
 struct SelectTargets {
   double th[kMaxThresholds];
@@ -166,16 +215,16 @@ __global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, cons
     // Python: int(threshold * num_elements) — a double product, truncated (generate_mask.py:69)
     long long k = (long long)(tg.th[j] * (double)numel);
     if (k > numel) k = numel;  // indices[:k] clamps
-    int64_t* out = select + ((size_t)seg * tg.n + j) * 2;
+    int64_t* out = select + ((size_t)seg * tg.n + j) * kSelFields;
     if (k <= 0) {
-      if (threadIdx.x == 0) { out[0] = -1; out[1] = 0; }
+      if (threadIdx.x == 0) write_select(out, -1, 0, 0);
       continue;
     }
     if ((unsigned long long)k > above0 && (unsigned long long)k <= above0 + local) {
       unsigned long long above = above0;
       for (int i = 0; i < 32; ++i) {
         const unsigned long long c = h[hi - i] - ((hi - i) == 0 ? pad : 0ull);
-        if ((unsigned long long)k <= above + c) { out[0] = hi - i; out[1] = (int64_t)((unsigned long long)k - above); break; }
+        if ((unsigned long long)k <= above + c) { write_select(out, hi - i, (int64_t)((unsigned long long)k - above), (int64_t)c); break; }
         above += c;
       }
     }
@@ -186,57 +235,135 @@ __global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, cons
 // Mask.  Chunks of 8192 elements never straddle tensors (chunk_prefix[s] = number of chunks before
 // tensor s).  Flat order inside a chunk is (iter, thread, lane-in-vector), loads stay coalesced.
 // ------------------------------------------------------------------------------------------------
-struct ChunkLoc {
-  int seg;
-  int64_t begin, end;  // element range of this chunk
-};
-__device__ __forceinline__ ChunkLoc locate_chunk(const int64_t* seg_off, const int64_t* chunk_prefix, int n_segs) {
-  const int64_t c = blockIdx.x;
+// One streaming pass (2 B read + 1 B written per parameter) with no communication between CTAs:
+//   mask_kernel   every chunk writes  key > tau -> 1  and counts its ties (key == tau).  Whether the ties
+//                 of a chunk are selected depends on how many ties precede it in the tensor, which the
+//                 chunk does not know yet; it SPECULATES from the histogram: ties are taken in chunks
+//                 before the point where `budget / total` of the tensor's chunks have passed.
+//   tie_scan      exclusive scan of the chunk tie counts per tensor (a few thousand numbers).
+//   tie_fix       every chunk checks its speculation against the exact prefix; the chunks that guessed
+//                 wrong (those between the guessed and the true boundary) and the one boundary chunk
+//                 are rewritten exactly, ties ranked in flat index order.
+// The result never depends on the speculation; only the amount of rewriting does (a handful of
+// chunks per tensor when ties are spread evenly, every chunk of a tensor in the worst case).
+constexpr int kCountShift = 48;  // scratch word = (chunk tie count << 48) | exclusive tie prefix
+
+__device__ __forceinline__ void locate_chunk(int64_t c, const int64_t* seg_off, const int64_t* chunk_prefix, int n_segs,
+                                             int& seg, int64_t& first_chunk, int64_t& begin, int64_t& end) {
   int lo = 0, hi = n_segs - 1;  // largest s with chunk_prefix[s] <= c
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
   }
-  ChunkLoc L;
-  L.seg = lo;
-  L.begin = seg_off[lo] + (c - chunk_prefix[lo]) * kChunk;
-  L.end = min(L.begin + (int64_t)kChunk, seg_off[lo + 1]);
-  return L;
+  seg = lo;
+  first_chunk = chunk_prefix[lo];
+  begin = seg_off[lo] + (c - first_chunk) * kChunk;
+  end = min(begin + (int64_t)kChunk, seg_off[lo + 1]);
 }
 
-__global__ void __launch_bounds__(kChunkThreads) tie_count_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
-                                                                  const int64_t* chunk_prefix, int n_segs,
-                                                                  const int64_t* select, int n_th, int th_index,
-                                                                  uint32_t* tie_count) {
-  __shared__ uint32_t red[kChunkThreads / 32];
-  const ChunkLoc L = locate_chunk(seg_off, chunk_prefix, n_segs);
-  const int64_t tau = select[((size_t)L.seg * n_th + th_index) * 2];
-  uint32_t cnt = 0;
-  if (tau >= 0) {
-#pragma unroll
-    for (int it = 0; it < kChunkIters; ++it) {
-      const int64_t e = L.begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
-      if (e < L.end) {
-        uint32_t k[8];
-        keys8(ld_stream(acc + e), k);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cnt += (k[j] == (uint32_t)tau);
+// Speculation: chunk number `rel` of `n` takes its ties iff rel / n < budget / total.
+__device__ __forceinline__ bool speculate_take(int64_t rel, int64_t n, int64_t budget, int64_t total) {
+  return (unsigned long long)rel * (unsigned long long)total < (unsigned long long)budget * (unsigned long long)n;
+}
+
+// Exact rewrite of one chunk given the number of ties before it.  Called by a whole CTA.
+__device__ __noinline__ void mask_ranked_chunk(const __nv_bfloat16* acc, int64_t begin, int64_t end, uint32_t lo2,
+                                               uint32_t hi2, unsigned long long prefix, unsigned long long budget,
+                                               uint32_t* wcnt /* [kChunkIters][kChunkThreads / 32] */, int8_t* mask) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kChunkThreads / 32;
+  uint32_t before[kChunkIters];
+  for (int it = 0; it < kChunkIters; ++it) {
+    const int64_t e = begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
+    uint32_t cnt = 0;
+    if (e < end) {
+      const uint4 raw = ld_stream(acc + e);
+      const uint32_t w[4] = {raw.x & 0x7FFF7FFFu, raw.y & 0x7FFF7FFFu, raw.z & 0x7FFF7FFFu, raw.w & 0x7FFF7FFFu};
+      for (int q = 0; q < 4; ++q) cnt += __popc(__vcmpgeu2(w[q], lo2) & ~__vcmpgtu2(w[q], hi2) & 0x00010001u);
+    }
+    uint32_t incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    before[it] = incl - cnt;
+    if (lane == 31) wcnt[it * kWarps + warp] = incl;
+  }
+  __syncthreads();
+  unsigned long long run = prefix;
+  for (int it = 0; it < kChunkIters; ++it) {
+    unsigned long long rank = run + before[it];
+    for (int w = 0; w < kWarps; ++w) {
+      if (w < warp) rank += wcnt[it * kWarps + w];
+      run += wcnt[it * kWarps + w];
+    }
+    const int64_t e = begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
+    if (e < end) {
+      const uint4 raw = ld_stream(acc + e);
+      const uint32_t w[4] = {raw.x & 0x7FFF7FFFu, raw.y & 0x7FFF7FFFu, raw.z & 0x7FFF7FFFu, raw.w & 0x7FFF7FFFu};
+      uint32_t sel01[4];
+      for (int q = 0; q < 4; ++q) {  // element 2q is the low half of word q, 2q + 1 the high half
+        const uint32_t g = __vcmpgtu2(w[q], hi2);
+        const uint32_t t = __vcmpgeu2(w[q], lo2) & ~g;
+        uint32_t kp = 0;
+        if (t & 0x0000FFFFu) { if (rank < budget) kp |= 0x0000FFFFu; ++rank; }
+        if (t & 0xFFFF0000u) { if (rank < budget) kp |= 0xFFFF0000u; ++rank; }
+        sel01[q] = (g | kp) & 0x00010001u;
       }
+      *reinterpret_cast<uint2*>(mask + e) =
+          make_uint2(__byte_perm(sel01[0], sel01[1], 0x6420), __byte_perm(sel01[2], sel01[3], 0x6420));
     }
   }
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();  // wcnt may be reused by the caller's next chunk
+}
+
+__global__ void __launch_bounds__(kChunkThreads, 4) mask_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
+                                                                const int64_t* chunk_prefix, int n_segs, const int64_t* select,
+                                                                int n_th, int th_index, unsigned long long* scratch,
+                                                                int8_t* mask) {
+  __shared__ uint32_t wsum[kChunkThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = blockIdx.x;
+  int seg;
+  int64_t first_chunk, begin, end;
+  locate_chunk(c, seg_off, chunk_prefix, n_segs, seg, first_chunk, begin, end);
+  const int64_t* sel = select + ((size_t)seg * n_th + th_index) * kSelFields;
+  const uint32_t plo = (uint32_t)sel[2], phi = (uint32_t)sel[3];
+  const uint32_t lo2 = plo | (plo << 16), hi2 = phi | (phi << 16);
+  const uint32_t take_all =
+      speculate_take(c - first_chunk, chunk_prefix[seg + 1] - first_chunk, sel[1], sel[4]) ? 0xFFFFFFFFu : 0u;
+
+  uint32_t mine = 0;
+#pragma unroll
+  for (int it = 0; it < kChunkIters; ++it) {
+    const int64_t e = begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
+    if (e < end) {
+      const uint4 raw = ld_stream(acc + e);
+      const uint32_t w[4] = {raw.x & 0x7FFF7FFFu, raw.y & 0x7FFF7FFFu, raw.z & 0x7FFF7FFFu, raw.w & 0x7FFF7FFFu};
+      uint32_t sel01[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // per 32-bit word (two elements): gt = pattern > hi, tie = lo <= pattern <= hi
+        const uint32_t g = __vcmpgtu2(w[q], hi2);
+        const uint32_t t = __vcmpgeu2(w[q], lo2) & ~g;
+        mine += __popc(t & 0x00010001u);
+        sel01[q] = (g | (t & take_all)) & 0x00010001u;
+      }
+      *reinterpret_cast<uint2*>(mask + e) =
+          make_uint2(__byte_perm(sel01[0], sel01[1], 0x6420), __byte_perm(sel01[2], sel01[3], 0x6420));
+    }
+  }
+  const uint32_t tot = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) wsum[warp] = tot;
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < kChunkThreads / 32; ++w) t += red[w];
-    tie_count[blockIdx.x] = t;
+    unsigned long long chunk_ties = 0;
+    for (int w = 0; w < kChunkThreads / 32; ++w) chunk_ties += wsum[w];
+    scratch[c] = chunk_ties << kCountShift;
   }
 }
 
-// In-place exclusive scan of the chunk tie counts of each tensor (one CTA per tensor).  Counts are
-// clamped so a 32-bit prefix cannot overflow: a prefix beyond the tie budget selects nothing anyway.
-__global__ void __launch_bounds__(1024) tie_scan_kernel(const int64_t* chunk_prefix, uint32_t* tie_count) {
+// One CTA per tensor: scratch[c] = (count << 48) | (ties in earlier chunks of the tensor).
+__global__ void __launch_bounds__(1024) tie_scan_kernel(const int64_t* chunk_prefix, unsigned long long* scratch) {
   __shared__ unsigned long long carry;
   __shared__ unsigned long long wsum[32];
   const int64_t c0 = chunk_prefix[blockIdx.x], c1 = chunk_prefix[blockIdx.x + 1];
@@ -245,7 +372,8 @@ __global__ void __launch_bounds__(1024) tie_scan_kernel(const int64_t* chunk_pre
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t base = c0; base < c1; base += 1024) {
     const int64_t i = base + threadIdx.x;
-    const unsigned long long v = (i < c1) ? tie_count[i] : 0;
+    const unsigned long long word = (i < c1) ? scratch[i] : 0;
+    const unsigned long long v = word >> kCountShift;
     unsigned long long incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -257,68 +385,48 @@ __global__ void __launch_bounds__(1024) tie_scan_kernel(const int64_t* chunk_pre
     unsigned long long wb = 0;
     for (int w = 0; w < warp; ++w) wb += wsum[w];
     const unsigned long long excl = carry + wb + incl - v;
-    if (i < c1) tie_count[i] = (uint32_t)min(excl, (unsigned long long)0xFFFFFFFFull);
+    if (i < c1) scratch[i] = (v << kCountShift) | excl;
     __syncthreads();
     if (threadIdx.x == 1023) carry = excl + v;
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(kChunkThreads) mask_write_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
-                                                                   const int64_t* chunk_prefix, int n_segs,
-                                                                   const int64_t* select, int n_th, int th_index,
-                                                                   const uint32_t* tie_prefix, int8_t* mask) {
-  __shared__ uint32_t wcnt[kChunkIters][kChunkThreads / 32];
-  const ChunkLoc L = locate_chunk(seg_off, chunk_prefix, n_segs);
-  const int64_t* sel = select + ((size_t)L.seg * n_th + th_index) * 2;
-  const int64_t tau = sel[0];
-  const unsigned long long budget = (unsigned long long)sel[1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  uint32_t k[kChunkIters][8];
-  uint32_t mine[kChunkIters];   // ties held by this thread per iteration
-  uint32_t before[kChunkIters]; // ties in lower lanes of this warp, same iteration
-#pragma unroll
-  for (int it = 0; it < kChunkIters; ++it) {
-    const int64_t e = L.begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
-    mine[it] = 0;
-    if (e < L.end) {
-      keys8(ld_stream(acc + e), k[it]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mine[it] += (tau >= 0 && k[it][j] == (uint32_t)tau);
-    }
-    uint32_t incl = mine[it];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
-    }
-    before[it] = incl - mine[it];
-    if (lane == 31) wcnt[it][warp] = incl;
+// Thread t of CTA b audits chunk b * 256 + t; the CTA then rewrites the chunks that guessed wrong.
+__global__ void __launch_bounds__(kChunkThreads) tie_fix_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
+                                                                const int64_t* chunk_prefix, int n_segs, int64_t n_chunks,
+                                                                const int64_t* select, int n_th, int th_index,
+                                                                const unsigned long long* scratch, int8_t* mask) {
+  __shared__ uint32_t wcnt[kChunkIters * (kChunkThreads / 32)];
+  __shared__ int n_wrong;
+  __shared__ int wrong[kChunkThreads];
+  if (threadIdx.x == 0) n_wrong = 0;
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * kChunkThreads + threadIdx.x;
+  if (c < n_chunks) {
+    int seg;
+    int64_t first_chunk, begin, end;
+    locate_chunk(c, seg_off, chunk_prefix, n_segs, seg, first_chunk, begin, end);
+    const int64_t* sel = select + ((size_t)seg * n_th + th_index) * kSelFields;
+    const unsigned long long budget = (unsigned long long)sel[1];
+    const unsigned long long word = scratch[c];
+    const unsigned long long cnt = word >> kCountShift, prefix = word & ((1ull << kCountShift) - 1);
+    const bool spec = speculate_take(c - first_chunk, chunk_prefix[seg + 1] - first_chunk, sel[1], sel[4]);
+    const bool all = prefix + cnt <= budget, none = prefix >= budget;
+    const bool ok = cnt == 0 || (spec ? all : none);
+    if (!ok) wrong[atomicAdd(&n_wrong, 1)] = (int)threadIdx.x;
   }
   __syncthreads();
-  unsigned long long run = tie_prefix[blockIdx.x];  // ties of this tensor in earlier chunks
-#pragma unroll
-  for (int it = 0; it < kChunkIters; ++it) {
-    unsigned long long rank = run + before[it];
-    for (int w = 0; w < kChunkThreads / 32; ++w) {
-      if (w < warp) rank += wcnt[it][w];
-      run += wcnt[it][w];
-    }
-    const int64_t e = L.begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
-    if (e < L.end) {
-      uint32_t lo = 0, hi = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t bit;
-        if (tau < 0) bit = 0;
-        else if (k[it][j] > (uint32_t)tau) bit = 1;
-        else if (k[it][j] == (uint32_t)tau) { bit = (rank < budget) ? 1u : 0u; ++rank; }
-        else bit = 0;
-        if (j < 4) lo |= bit << (8 * j); else hi |= bit << (8 * (j - 4));
-      }
-      *reinterpret_cast<uint2*>(mask + e) = make_uint2(lo, hi);
-    }
+  const int nw = n_wrong;
+  for (int i = 0; i < nw; ++i) {  // block-uniform loop
+    const int64_t cw = (int64_t)blockIdx.x * kChunkThreads + wrong[i];
+    int seg;
+    int64_t first_chunk, begin, end;
+    locate_chunk(cw, seg_off, chunk_prefix, n_segs, seg, first_chunk, begin, end);
+    const int64_t* sel = select + ((size_t)seg * n_th + th_index) * kSelFields;
+    const uint32_t plo = (uint32_t)sel[2], phi = (uint32_t)sel[3];
+    mask_ranked_chunk(acc, begin, end, plo | (plo << 16), phi | (phi << 16), scratch[cw] & ((1ull << kCountShift) - 1),
+                      (unsigned long long)sel[1], wcnt, mask);
   }
 }
 
@@ -338,36 +446,59 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
   p = __fmul_rn(p, c.decay);                                        // param.mul_(1 - lr * wd)
   m = __fadd_rn(m, __fmul_rn(c.w1, __fsub_rn(g, m)));               // exp_avg.lerp_(grad, 1 - beta1)
   v = __fadd_rn(__fmul_rn(v, c.beta2), __fmul_rn(c.w2, __fmul_rn(g, g)));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
-  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
-  return __fsub_rn(p, __fmul_rn(c.step_size, __fdiv_rn(m, denom)));   // addcdiv_(exp_avg, denom, -step_size)
+  // The IEEE square root / division take a slow path (a subroutine call, the whole warp with it) when an
+  // operand is zero — which every masked-out parameter is, forever.  A zero operand is swapped for 1 and
+  // the exact result (sqrt(+0) = +0, +-0 / d = +-0) selected afterwards: same bits, fast path.
+  const float sq = (v == 0.f) ? v : __fsqrt_rn((v == 0.f) ? 1.f : v);
+  const float sd = (sq == 0.f) ? sq : __fdiv_rn((sq == 0.f) ? 1.f : sq, c.bc2_sqrt);
+  const float denom = __fadd_rn(sd, c.eps);
+  const float q = (m == 0.f) ? __fmul_rn(m, 1.f) : __fdiv_rn((m == 0.f) ? 1.f : m, denom);
+  return __fsub_rn(p, __fmul_rn(c.step_size, q));   // addcdiv_(exp_avg, denom, -step_size)
 }
+
+constexpr int kAdamVecs = 1;  // 128-bit parameter vectors per thread and iteration (loads issued before any math)
 
 __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const __nv_bfloat16* grad, float* exp_avg,
                                                     float* exp_avg_sq, const int8_t* mask, int64_t n, AdamConsts c) {
   const int64_t nvec = n >> 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    uint4 pr = reinterpret_cast<const uint4*>(param)[i];
-    const uint4 gr = ld_stream(reinterpret_cast<const uint4*>(grad) + i);
-    float4 m0 = reinterpret_cast<const float4*>(exp_avg)[2 * i], m1 = reinterpret_cast<const float4*>(exp_avg)[2 * i + 1];
-    float4 v0 = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i], v1 = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i + 1];
-    uint2 mk = make_uint2(0x01010101u, 0x01010101u);
-    if (mask) mk = *reinterpret_cast<const uint2*>(mask + (i << 3));
-    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(&pr);
-    const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&gr);
-    float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-    float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kAdamVecs) {
+    uint4 pr[kAdamVecs], gr[kAdamVecs];
+    float4 m0[kAdamVecs], m1[kAdamVecs], v0[kAdamVecs], v1[kAdamVecs];
+    uint2 mk[kAdamVecs];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t mb = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xFFu;
-      const float g = mb ? __bfloat162float(gh[j]) : 0.f;  // grad *= mask
-      ph[j] = __float2bfloat16_rn(adam_one(__bfloat162float(ph[j]), g, mm[j], vv[j], c));
+    for (int u = 0; u < kAdamVecs; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < nvec) {
+        pr[u] = reinterpret_cast<const uint4*>(param)[i];
+        gr[u] = ld_stream(reinterpret_cast<const uint4*>(grad) + i);
+        m0[u] = reinterpret_cast<const float4*>(exp_avg)[2 * i];
+        m1[u] = reinterpret_cast<const float4*>(exp_avg)[2 * i + 1];
+        v0[u] = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i];
+        v1[u] = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i + 1];
+        mk[u] = mask ? *reinterpret_cast<const uint2*>(mask + (i << 3)) : make_uint2(0x01010101u, 0x01010101u);
+      }
     }
-    reinterpret_cast<uint4*>(param)[i] = pr;
-    reinterpret_cast<float4*>(exp_avg)[2 * i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    reinterpret_cast<float4*>(exp_avg)[2 * i + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
-    reinterpret_cast<float4*>(exp_avg_sq)[2 * i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    reinterpret_cast<float4*>(exp_avg_sq)[2 * i + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+#pragma unroll
+    for (int u = 0; u < kAdamVecs; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= nvec) break;
+      __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(&pr[u]);
+      const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&gr[u]);
+      float mm[8] = {m0[u].x, m0[u].y, m0[u].z, m0[u].w, m1[u].x, m1[u].y, m1[u].z, m1[u].w};
+      float vv[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t mb = ((j < 4 ? mk[u].x : mk[u].y) >> (8 * (j & 3))) & 0xFFu;
+        const float g = mb ? __bfloat162float(gh[j]) : 0.f;  // grad *= mask
+        ph[j] = __float2bfloat16_rn(adam_one(__bfloat162float(ph[j]), g, mm[j], vv[j], c));
+      }
+      reinterpret_cast<uint4*>(param)[i] = pr[u];
+      reinterpret_cast<float4*>(exp_avg)[2 * i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(exp_avg)[2 * i + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
+      reinterpret_cast<float4*>(exp_avg_sq)[2 * i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      reinterpret_cast<float4*>(exp_avg_sq)[2 * i + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int64_t i = nvec << 3; i < n; ++i) {
@@ -418,7 +549,7 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
   int64_t blocks = sms > 0 ? sms : 148;
   int64_t per_block = ((n_total + blocks - 1) / blocks + 4095) / 4096 * 4096;
   blocks = (n_total + per_block - 1) / per_block;
-  histogram_kernel<<<(unsigned)blocks, 512, kBins * 4, static_cast<cudaStream_t>(stream)>>>(
+  histogram_kernel<<<(unsigned)blocks, kHistThreads, kBins * 4, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(acc), seg_offsets_dev, n_segs, n_total, per_block, hist);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
@@ -440,20 +571,21 @@ int64_t clear_saliency_chunk_elems(void) { return kChunk; }
 
 int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
                         int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
-                        uint32_t* tie_scratch, int8_t* mask, void* stream_) {
+                        uint64_t* tie_scratch, int8_t* mask, void* stream_) {
   if (!acc || !seg_offsets_dev || !chunk_prefix_dev || !select || !tie_scratch || !mask)
     return fail(CLEAR_ERR_NULL, "clear_saliency_mask: null pointer");
   if (n_segs <= 0 || n_chunks <= 0 || n_chunks > INT32_MAX || th_index < 0 || th_index >= n_th)
     return fail(CLEAR_ERR_SHAPE, "clear_saliency_mask: bad sizes");
-  if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(mask) & 7))
-    return fail(CLEAR_ERR_ALIGN, "clear_saliency_mask: acc must be 16-byte and mask 8-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(mask) & 7) || (reinterpret_cast<uintptr_t>(tie_scratch) & 7))
+    return fail(CLEAR_ERR_ALIGN, "clear_saliency_mask: acc must be 16-byte, mask and tie_scratch 8-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(acc);
-  tie_count_kernel<<<(unsigned)n_chunks, kChunkThreads, 0, stream>>>(a, seg_offsets_dev, chunk_prefix_dev, n_segs, select,
-                                                                    n_th, th_index, tie_scratch);
-  tie_scan_kernel<<<(unsigned)n_segs, 1024, 0, stream>>>(chunk_prefix_dev, tie_scratch);
-  mask_write_kernel<<<(unsigned)n_chunks, kChunkThreads, 0, stream>>>(a, seg_offsets_dev, chunk_prefix_dev, n_segs, select,
-                                                                     n_th, th_index, tie_scratch, mask);
+  unsigned long long* scratch = reinterpret_cast<unsigned long long*>(tie_scratch);
+  mask_kernel<<<(unsigned)n_chunks, kChunkThreads, 0, stream>>>(a, seg_offsets_dev, chunk_prefix_dev, n_segs, select, n_th,
+                                                               th_index, scratch, mask);
+  tie_scan_kernel<<<(unsigned)n_segs, 1024, 0, stream>>>(chunk_prefix_dev, scratch);
+  tie_fix_kernel<<<(unsigned)((n_chunks + kChunkThreads - 1) / kChunkThreads), kChunkThreads, 0, stream>>>(
+      a, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th, th_index, scratch, mask);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }

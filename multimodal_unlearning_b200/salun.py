@@ -102,7 +102,8 @@ class SaliencyState:
 
     # ---- generate_mask.py:47-85 -------------------------------------------------------------------
     def select(self, thresholds: Sequence[float] = REFERENCE_THRESHOLDS) -> torch.Tensor:
-        """Per tensor and threshold: (bit pattern of the k-th largest key, ties to take).  int64 [S, n_th, 2]."""
+        """Per tensor and threshold: (bit pattern tau of the k-th largest key, ties to take, lo, hi) with
+        [lo, hi] the bf16 magnitude patterns whose key is tau, total = #{key == tau}).  int64 [S, n_th, 5]."""
         lib = _lib.load()
         lay = self.layout
         n_segs = len(lay.names)
@@ -110,7 +111,7 @@ class SaliencyState:
         _lib.check(lib.clear_saliency_histogram(self.acc.data_ptr(), self.seg_off.data_ptr(), n_segs, lay.total,
                                                 hist.data_ptr(), _stream()), "clear_saliency_histogram")
         th = (C.c_double * len(thresholds))(*[float(t) for t in thresholds])
-        sel = torch.full((n_segs, len(thresholds), 2), -1, dtype=torch.int64, device=self.device)
+        sel = torch.full((n_segs, len(thresholds), 5), -1, dtype=torch.int64, device=self.device)
         _lib.check(lib.clear_saliency_select(hist.data_ptr(), self.seg_off.data_ptr(), self.seg_numel.data_ptr(), n_segs,
                                              th, len(thresholds), sel.data_ptr(), _stream()), "clear_saliency_select")
         self.launches += 2
@@ -123,7 +124,7 @@ class SaliencyState:
         lay = self.layout
         if out is None:
             out = torch.empty(lay.total, dtype=torch.int8, device=self.device)
-        scratch = torch.empty(lay.n_chunks, dtype=torch.int32, device=self.device)
+        scratch = torch.empty(lay.n_chunks + 1, dtype=torch.int64, device=self.device)
         _lib.check(lib.clear_saliency_mask(self.acc.data_ptr(), self.seg_off.data_ptr(), self.chunk_prefix.data_ptr(),
                                            len(lay.names), lay.n_chunks, sel.data_ptr(), sel.shape[1], th_index,
                                            scratch.data_ptr(), out.data_ptr(), _stream()), "clear_saliency_mask")

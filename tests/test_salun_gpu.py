@@ -76,8 +76,17 @@ def test_ties_odd_sizes_and_special_values():
     sel = state.select(ths).cpu().numpy()
     for i, n in enumerate(layout.names):
         keys = SO.saliency_keys(named[n])
+        pat = torch.arange(0x8000, dtype=torch.int16).view(torch.bfloat16)
+        key_of_pattern = SO.saliency_keys(pat)        # key of every bf16 magnitude bit pattern
         for j, th in enumerate(ths):
-            assert tuple(sel[i, j]) == SO.select(keys, th), (n, th)
+            tau, ties = SO.select(keys, th)
+            assert (int(sel[i, j, 0]), int(sel[i, j, 1])) == (tau, ties), (n, th)
+            lo, hi = int(sel[i, j, 2]), int(sel[i, j, 3])
+            if tau < 0:
+                assert lo > 0x7FFF and hi >= 0x7FFF   # nothing above hi, nothing inside [lo, hi]
+            else:
+                inside = np.nonzero(key_of_pattern == tau)[0]
+                assert (lo, hi) == (int(inside.min()), int(inside.max())), (n, th)
 
 
 def test_accumulate_per_tensor_matches_flat():

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+CMD="python tools/bench_salun.py --layers 4 --reps 1"
+$CMD > gpurun_out/salun_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'histogram_kernel|mask_kernel|adamw_kernel' -c 8 -o gpurun_out/prof_salun $CMD > gpurun_out/ncu_salun.log 2>&1
+tail -3 gpurun_out/ncu_salun.log
