@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-salun", action="store_true", help="skip the SalUn mask / masked-AdamW HBM-roofline section")
+    ap.add_argument("--salun-layers", type=int, default=32, help="Llama-2-7B layer count of the synthetic parameter list")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
@@ -291,6 +293,21 @@ def main():
     gemm_launches = sum(v[0] for k, v in summ.items() if k.startswith("gemm")) // 3
     rowloss_ms = summ.get("rowloss", (0, 0.0))[1] / 3
 
+    # ---- SalUn mask + masked AdamW over all parameters of Llama-2-7B (BASELINE configs[3]); HBM roofline ----
+    salun_res = None
+    if world == 1 and not args.no_salun:
+        del bufs, h_hidden, h_ref
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import bench_salun
+            salun_res = bench_salun.run(layers=args.salun_layers, reps=3, peak_gbs=_peaks()["hbm_gbs"])
+            salun_res["workload"] = ("SalUn over the Llama-2-7B parameter list (synthetic bf16 grads 1e-3*randn): accumulate, "
+                                     "histogram+select for 10 thresholds, one int8 mask, one masked AdamW step; "
+                                     "frac = algorithmic bytes / time / measured HBM copy peak")
+        except Exception as e:  # never lose the head's line to the secondary section
+            salun_res = {"error": f"{type(e).__name__}: {e}"}
+
     # max over ranks
     t = torch.tensor([ms, ms_e2e, gemm_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -323,6 +340,7 @@ def main():
                          "step_frac": flops_step / (ms / args.steps * 1e-3) / 1e12 / peak,
                          "rowloss_ms_per_step": rowloss_ms},
             "cpu_baseline": cpu_base,
+            "salun_hbm_roofline": salun_res,
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -317,48 +317,92 @@ __device__ __noinline__ void mask_ranked_chunk(const __nv_bfloat16* acc, int64_t
   __syncthreads();  // wcnt may be reused by the caller's next chunk
 }
 
-__global__ void __launch_bounds__(kChunkThreads, 4) mask_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
-                                                                const int64_t* chunk_prefix, int n_segs, const int64_t* select,
-                                                                int n_th, int th_index, unsigned long long* scratch,
-                                                                int8_t* mask) {
-  __shared__ uint32_t wsum[kChunkThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t c = blockIdx.x;
-  int seg;
-  int64_t first_chunk, begin, end;
-  locate_chunk(c, seg_off, chunk_prefix, n_segs, seg, first_chunk, begin, end);
-  const int64_t* sel = select + ((size_t)seg * n_th + th_index) * kSelFields;
-  const uint32_t plo = (uint32_t)sel[2], phi = (uint32_t)sel[3];
-  const uint32_t lo2 = plo | (plo << 16), hi2 = phi | (phi << 16);
-  const uint32_t take_all =
-      speculate_take(c - first_chunk, chunk_prefix[seg + 1] - first_chunk, sel[1], sel[4]) ? 0xFFFFFFFFu : 0u;
+// Pattern comparisons two at a time.  Sign-stripped bf16 bit patterns order like the bf16 values they
+// encode, so `pattern > hi` is one HSET2.BF16 per word (the "unordered" forms treat NaN patterns, which
+// sit above infinity, as greater).  If a bound itself is a NaN pattern (a threshold that lands among NaN
+// keys) the integer SIMD comparison is used instead.
+template <bool kFloatCmp>
+__device__ __forceinline__ void cmp_word(uint32_t w, uint32_t lo2, uint32_t hi2, uint32_t& g, uint32_t& ge) {
+  if constexpr (kFloatCmp) {
+    const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&w);
+    g = __hgtu2_mask(x, *reinterpret_cast<const __nv_bfloat162*>(&hi2));
+    ge = __hgeu2_mask(x, *reinterpret_cast<const __nv_bfloat162*>(&lo2));
+  } else {
+    g = __vcmpgtu2(w, hi2);
+    ge = __vcmpgeu2(w, lo2);
+  }
+}
 
-  uint32_t mine = 0;
+constexpr int kChunksPerCta = 4;
+
+template <bool kFloatCmp>
+__device__ __forceinline__ uint32_t mask_chunk_fast(const __nv_bfloat16* acc, int64_t begin, int64_t end, uint32_t lo2,
+                                                    uint32_t hi2, uint32_t take_all, int8_t* mask) {
+  uint4 raw[kChunkIters];
+#pragma unroll
+  for (int it = 0; it < kChunkIters; ++it) {
+    const int64_t e = begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
+    raw[it] = (e < end) ? ld_stream(acc + e) : make_uint4(0, 0, 0, 0);
+  }
+  uint32_t packed = 0;  // two 16-bit tie counters
 #pragma unroll
   for (int it = 0; it < kChunkIters; ++it) {
     const int64_t e = begin + ((int64_t)it * kChunkThreads + threadIdx.x) * 8;
     if (e < end) {
-      const uint4 raw = ld_stream(acc + e);
-      const uint32_t w[4] = {raw.x & 0x7FFF7FFFu, raw.y & 0x7FFF7FFFu, raw.z & 0x7FFF7FFFu, raw.w & 0x7FFF7FFFu};
+      const uint32_t w[4] = {raw[it].x & 0x7FFF7FFFu, raw[it].y & 0x7FFF7FFFu, raw[it].z & 0x7FFF7FFFu, raw[it].w & 0x7FFF7FFFu};
       uint32_t sel01[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {  // per 32-bit word (two elements): gt = pattern > hi, tie = lo <= pattern <= hi
-        const uint32_t g = __vcmpgtu2(w[q], hi2);
-        const uint32_t t = __vcmpgeu2(w[q], lo2) & ~g;
-        mine += __popc(t & 0x00010001u);
-        sel01[q] = (g | (t & take_all)) & 0x00010001u;
+      for (int q = 0; q < 4; ++q) {  // per 32-bit word (two elements): g = pattern > hi, tie = lo <= pattern <= hi
+        uint32_t g, ge;
+        cmp_word<kFloatCmp>(w[q], lo2, hi2, g, ge);
+        const uint32_t t01 = ge & ~g & 0x00010001u;
+        packed += t01;
+        sel01[q] = (g & 0x00010001u) | (t01 & take_all);
       }
       *reinterpret_cast<uint2*>(mask + e) =
           make_uint2(__byte_perm(sel01[0], sel01[1], 0x6420), __byte_perm(sel01[2], sel01[3], 0x6420));
     }
   }
-  const uint32_t tot = __reduce_add_sync(0xffffffffu, mine);
-  if (lane == 0) wsum[warp] = tot;
+  return (packed & 0xFFFFu) + (packed >> 16);
+}
+
+__global__ void __launch_bounds__(kChunkThreads) mask_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
+                                                             const int64_t* chunk_prefix, int n_segs, int64_t n_chunks,
+                                                             const int64_t* select, int n_th, int th_index,
+                                                             unsigned long long* scratch, int8_t* mask) {
+  __shared__ uint32_t wsum[kChunksPerCta][kChunkThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * kChunksPerCta;
+  int seg;
+  int64_t first_chunk, begin, end;
+  locate_chunk(c0, seg_off, chunk_prefix, n_segs, seg, first_chunk, begin, end);
+  int64_t seg_last = chunk_prefix[seg + 1];  // one past the tensor's last chunk
+#pragma unroll 1
+  for (int i = 0; i < kChunksPerCta; ++i) {
+    const int64_t c = c0 + i;
+    if (c >= n_chunks) break;
+    if (c >= seg_last) {  // crossed into the next non-empty tensor
+      do { ++seg; } while (chunk_prefix[seg + 1] <= c);
+      first_chunk = chunk_prefix[seg];
+      seg_last = chunk_prefix[seg + 1];
+    }
+    begin = seg_off[seg] + (c - first_chunk) * kChunk;
+    end = min(begin + (int64_t)kChunk, seg_off[seg + 1]);
+    const int64_t* sel = select + ((size_t)seg * n_th + th_index) * kSelFields;
+    const uint32_t plo = (uint32_t)sel[2], phi = (uint32_t)sel[3];
+    const uint32_t lo2 = plo | (plo << 16), hi2 = phi | (phi << 16);
+    const uint32_t take_all = speculate_take(c - first_chunk, seg_last - first_chunk, sel[1], sel[4]) ? 0xFFFFFFFFu : 0u;
+    const bool float_ok = plo <= 0x7F80u && phi <= 0x7F80u;  // block-uniform
+    const uint32_t mine = float_ok ? mask_chunk_fast<true>(acc, begin, end, lo2, hi2, take_all, mask)
+                                   : mask_chunk_fast<false>(acc, begin, end, lo2, hi2, take_all, mask);
+    const uint32_t tot = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) wsum[i][warp] = tot;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < kChunksPerCta && c0 + threadIdx.x < n_chunks) {
     unsigned long long chunk_ties = 0;
-    for (int w = 0; w < kChunkThreads / 32; ++w) chunk_ties += wsum[w];
-    scratch[c] = chunk_ties << kCountShift;
+    for (int w = 0; w < kChunkThreads / 32; ++w) chunk_ties += wsum[threadIdx.x][w];
+    scratch[c0 + threadIdx.x] = chunk_ties << kCountShift;
   }
 }
 
@@ -581,8 +625,8 @@ int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(acc);
   unsigned long long* scratch = reinterpret_cast<unsigned long long*>(tie_scratch);
-  mask_kernel<<<(unsigned)n_chunks, kChunkThreads, 0, stream>>>(a, seg_offsets_dev, chunk_prefix_dev, n_segs, select, n_th,
-                                                               th_index, scratch, mask);
+  mask_kernel<<<(unsigned)((n_chunks + kChunksPerCta - 1) / kChunksPerCta), kChunkThreads, 0, stream>>>(
+      a, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th, th_index, scratch, mask);
   tie_scan_kernel<<<(unsigned)n_segs, 1024, 0, stream>>>(chunk_prefix_dev, scratch);
   tie_fix_kernel<<<(unsigned)((n_chunks + kChunkThreads - 1) / kChunkThreads), kChunkThreads, 0, stream>>>(
       a, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th, th_index, scratch, mask);
