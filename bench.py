@@ -55,7 +55,7 @@ def _peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -75,7 +75,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this call are reported."""
+        self.t_mark = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -87,7 +91,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, ln in self.lines:
+            if ts < t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -129,7 +136,7 @@ def cpu_reference_rate(sample_rows: int, reps: int):
 def run_reference_arm(args, rank: int):
     if rank != 0:
         return
-    rows = 256
+    rows = 2048
     total = 0.0
     times = []
     rate, cores, _ = cpu_reference_rate(rows, 1)  # warm-up of allocator / thread pool
@@ -189,9 +196,9 @@ def main():
     # CPU baseline first (rank 0, N=1 only), before the GPU is busy
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, best = cpu_reference_rate(256, 3)
+        rate, cores, best = cpu_reference_rate(2048, 3)
         cpu_base = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"256 of 8192 rows, best of 3, fp32 torch CPU eager: lm_head + mm NPO + backward ({best:.2f} s)"}
+                    "sample": f"2048 of 8192 rows, best of 3, fp32 torch CPU eager: lm_head + mm NPO + backward ({best:.2f} s per pass)"}
 
     # synthetic inputs
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -218,15 +225,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a moment to start: launched before the warm-up, marked at the timed region
     for i in range(args.warmup):
         res = step(i, hidden, ref_hidden)
     barrier()
     launches_per_step = res.launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if rank == 0:
+        sampler.mark()
     e0.record()
     for i in range(args.steps):
         res = step(i, hidden, ref_hidden)

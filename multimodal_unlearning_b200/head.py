@@ -220,7 +220,7 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
                       reduction: str = "reference", n_seqs: int | None = None,
                       row_weight: torch.Tensor | None = None, need_dhidden: bool = True, need_dweight: bool = True,
                       dweight_accum: torch.Tensor | None = None, block_rows: int | None = None,
-                      cta_group: int = 0) -> HeadResult:
+                      cta_group: int = 0, overlap: bool = False) -> HeadResult:
     """One head invocation: loss = coef * norm * sum_i term_i, plus d loss/d hidden and d loss/d weight.
 
     hidden [N, H] bf16, weight [V, H] bf16; labels [N] int64 ALREADY SHIFTED (see shift_labels) for CE;
@@ -229,6 +229,8 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     dweight_accum: optional fp32 [V, H] buffer; dW is ADDED into it (gradient accumulation across
     splits / micro-batches happens in fp32 inside the contraction's epilogue) and returned as is.
     need_dhidden = need_dweight = False gives the forward-only mode (no dlogits are written).
+    overlap: issue the contractions and the row passes on two streams (see the staging comment below).  Off
+    by default: under the 1 kW power cap the step is energy-bound and the overlap measured no gain on B200.
     """
     lib = _lib.load()
     hidden = _check_2d_bf16(hidden, "hidden")
@@ -280,8 +282,14 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         count_valid(labels, inv_count)
         launches += 1
 
-    z = torch.empty((blk, ld), dtype=torch.bfloat16, device=dev)
-    part = torch.empty((blk, nt, 2), dtype=torch.float32, device=dev)
+    # Staging: two student blocks (block b+1 is projected while block b is still being consumed) and one
+    # teacher block.  The row pass is bound by the XU pipe and HBM, the contractions by the tensor pipe, so
+    # they are issued on two streams and overlap: row pass of block b runs beside the student projection of
+    # block b+1 and beside the backward contractions of block b-1.
+    pipelined = overlap and n_blocks >= 2 and StageTimer.active is None
+    n_stage = 2 if pipelined else 1
+    zs = [torch.empty((blk, ld), dtype=torch.bfloat16, device=dev) for _ in range(n_stage)]
+    parts = [torch.empty((blk, nt, 2), dtype=torch.float32, device=dev) for _ in range(n_stage)]
     zr = rpart = None
     if needs_ref:
         rpart = torch.empty((blk, nt, 2), dtype=torch.float32, device=dev)
@@ -300,34 +308,70 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         else:
             dweight = torch.empty(weight.shape, dtype=torch.float32, device=dev)
 
-    for b in range(n_blocks):
+    def block(b):
         r0, r1 = b * blk, min(n, (b + 1) * blk)
-        rows = r1 - r0
-        hb = hidden[r0:r1]
-        zb, pb = z[:rows], part[:rows]
-        project(hb, weight, zb, pb, cta_group)
-        launches += 1
+        return r0, r1, zs[b % n_stage][: r1 - r0], parts[b % n_stage][: r1 - r0]
+
+    def do_project(b):
+        r0, r1, zb, pb = block(b)
+        project(hidden[r0:r1], weight, zb, pb, cta_group)
+
+    def do_teacher(b):
+        r0, r1, _, _ = block(b)
+        if ref_logits is None:
+            project(ref_hidden[r0:r1], ref_weight, zr[: r1 - r0], rpart[: r1 - r0], cta_group)
+        else:
+            _ref_lse(ref_logits[r0:r1], rpart[: r1 - r0], v)
+
+    def do_rowloss(b):
+        r0, r1, zb, pb = block(b)
         zrb = rpb = None
         if needs_ref:
-            rpb = rpart[:rows]
-            if ref_logits is None:
-                zrb = zr[:rows]
-                project(ref_hidden[r0:r1], ref_weight, zrb, rpb, cta_group)
-                launches += 1
-            else:
-                zrb = ref_logits[r0:r1]
-                _ref_lse(zrb, rpb, v)
-                launches += 1
+            rpb = rpart[: r1 - r0]
+            zrb = zr[: r1 - r0] if ref_logits is None else ref_logits[r0:r1]
         rowloss(kind, zb, pb, loss_rows[r0:r1], v, ref_logits=zrb, ref_lse_part=rpb,
                 labels=labels[r0:r1] if labels is not None and kind == KIND_CE else None,
                 row_weight=row_weight[r0:r1] if row_weight is not None else None, scale_dev=inv_count,
                 grad_scale=coef * grad_scale, beta=beta, write_grad=write_grad)
-        launches += 1
-        if write_grad:
-            acc = (dweight_accum is not None) or b > 0
-            backward(zb, v, hb, weight, dhidden[r0:r1] if need_dhidden else None,
-                     dweight if need_dweight else None, accumulate=acc, cta_group=cta_group)
-            launches += int(need_dhidden) + int(need_dweight)
+
+    def do_backward(b):
+        r0, r1, zb, _ = block(b)
+        backward(zb, v, hidden[r0:r1], weight, dhidden[r0:r1] if need_dhidden else None,
+                 dweight if need_dweight else None, accumulate=(dweight_accum is not None) or b > 0, cta_group=cta_group)
+
+    launches += n_blocks * (2 + int(needs_ref) + (int(need_dhidden) + int(need_dweight) if write_grad else 0))
+    if not pipelined:
+        for b in range(n_blocks):
+            do_project(b)
+            if needs_ref:
+                do_teacher(b)
+            do_rowloss(b)
+            if write_grad:
+                do_backward(b)
+    else:
+        main = torch.cuda.current_stream()
+        gs = _gemm_stream(dev)
+        gs.wait_stream(main)
+        row_done = [None] * n_blocks
+        for b in range(n_blocks + 1):
+            if b < n_blocks:
+                with torch.cuda.stream(gs):
+                    do_project(b)                                   # beside the row pass of block b-1
+                    if needs_ref:
+                        if b >= 1:
+                            gs.wait_event(row_done[b - 1])          # the teacher block is free again
+                        do_teacher(b)
+                    projected = torch.cuda.Event()
+                    projected.record(gs)
+                main.wait_event(projected)
+                do_rowloss(b)                                       # beside the backward of block b-1
+                row_done[b] = torch.cuda.Event()
+                row_done[b].record(main)
+            if b >= 1 and write_grad:
+                with torch.cuda.stream(gs):
+                    gs.wait_event(row_done[b - 1])
+                    do_backward(b - 1)
+        main.wait_stream(gs)
 
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     reduce_rows(loss_rows, loss, coef * host_scale, inv_count)
@@ -343,6 +387,17 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         dweight = dweight.to(torch.bfloat16)
     del lib
     return HeadResult(loss, seq_loss, dhidden, dweight, loss_rows, launches)
+
+
+_GEMM_STREAMS: dict = {}
+
+
+def _gemm_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """High-priority side stream for the contractions (one per device)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _GEMM_STREAMS:
+        _GEMM_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _GEMM_STREAMS[key]
 
 
 def _ref_lse(ref_logits: torch.Tensor, lse_part: torch.Tensor, vocab: int) -> None:

@@ -146,9 +146,9 @@ def test_fused_head_vs_oracle(kind, shape):
     coef = -0.7
     hid, w, rh, rw, y = _inputs(n, h, v, 20 + kind, dev)
     want_loss, want_dh, want_dw = _oracle_fused(kind, hid, w, rh, rw, y, beta, coef)
-    for block_rows in (None, 128):
+    for block_rows, overlap in ((None, False), (128, False), (128, True)):
         res = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), kind, labels=y.to(dev), ref_hidden=rh.to(dev),
-                                     ref_weight=rw.to(dev), beta=beta, coef=coef, block_rows=block_rows)
+                                     ref_weight=rw.to(dev), beta=beta, coef=coef, block_rows=block_rows, overlap=overlap)
         torch.cuda.synchronize()
         assert abs(res.loss.item() - want_loss.item()) <= LOSS_RTOL * abs(want_loss.item()), (res.loss.item(), want_loss.item())
         _assert_grad(res.dhidden, want_dh, f"dH kind {kind} block {block_rows}")
