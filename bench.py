@@ -237,13 +237,15 @@ def main():
     if rank == 0:
         sampler.mark()
     e0.record()
-    for i in range(args.steps):
-        res = step(i, hidden, ref_hidden)
-    for r_h in dws:
-        if r_h is not None:
-            reducer.wait(r_h[1])
-    e1.record()
-    barrier()
+    with head.StageTimer() as st:   # CUDA events around every launch of the timed region (the live roofline numbers)
+        for i in range(args.steps):
+            res = step(i, hidden, ref_hidden)
+        for r_h in dws:
+            if r_h is not None:
+                reducer.wait(r_h[1])
+        e1.record()
+        barrier()
+    summ = st.summary()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     loss_value = res.loss.item()
@@ -292,15 +294,10 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    # ---- live roofline of the dominant kernel (tcgen05 contraction), CUDA events around each launch -
-    with head.StageTimer() as st:
-        for i in range(3):
-            head.head_loss_fwd_bwd(hidden, weight, KIND_NPO, ref_hidden=ref_hidden, ref_weight=ref_weight, beta=BETA,
-                                   block_rows=block_rows)
-    summ = st.summary()
-    gemm_ms = sum(v[1] for k, v in summ.items() if k.startswith("gemm")) / 3
-    gemm_launches = sum(v[0] for k, v in summ.items() if k.startswith("gemm")) // 3
-    rowloss_ms = summ.get("rowloss", (0, 0.0))[1] / 3
+    # ---- live roofline of the dominant kernel (tcgen05 contraction): events recorded inside the timed region ----
+    gemm_ms = sum(v[1] for k, v in summ.items() if k.startswith("gemm")) / args.steps
+    gemm_launches = sum(v[0] for k, v in summ.items() if k.startswith("gemm")) // args.steps
+    rowloss_ms = summ.get("rowloss", (0, 0.0))[1] / args.steps
 
     # ---- SalUn mask + masked AdamW over all parameters of Llama-2-7B (BASELINE configs[3]); HBM roofline ----
     salun_res = None
@@ -336,13 +333,14 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "loss_type": "npo", "rows_per_gpu": n, "hidden": H, "vocab": V,
                        "block_rows": block_rows or head.DEFAULT_BLOCK_ROWS, "loss": loss_value,
-                       "l2": "inputs larger than L2 (W 263 MB + staged logits 2 x 263 MB per block vs 126 MB L2); no explicit flush",
+                       "l2": "inputs larger than L2 (W 263 MB + hidden 2 x 67 MB + staged logits 2 x 525 MB vs 126 MB L2); no explicit flush",
                        "dw_allreduce": "NCCL all-reduce(avg) of bf16 dW per step, overlapped with the next step" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05, cta_group::2)",
+                         "traffic": 0.92e9, "traffic_note": "dram bytes read+written per launch, mean of the 4 contraction launches of a block, ncu --set full at 4096-row blocks (profiles/r01_head_ncu_summary.md); algorithmic operand+result bytes per launch 0.56 GB",
+                         "kernel": "gemm_bf16_kernel (tcgen05, cta_group::2)",
                          "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
                          "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                          "frac_of_burst_peak": achieved / peaks["tflops_burst"],

@@ -62,7 +62,8 @@ int clear_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * tests and the roofline benchmark can drive each operand layout directly.
  *   a_major / b_major: 0 = K-major  (operand stored row-major as [M or N, K], ld = row stride)
  *                      1 = MN-major (operand stored row-major as [K, M or N], ld = row stride)
- *   d_f32: 0 -> D is bf16, 1 -> D is fp32;  accumulate (fp32 only): D += instead of D =
+ *   d_f32: 0 -> D is bf16, 1 -> D is fp32;  accumulate: D += instead of D = (TMA reduce-add; a bf16 D is
+ *          rounded to bf16 after each add)
  *   lse_part: optional float2[M][ceil(N/256)] = (row max, sum exp(x - max)) over each 256-column
  *             tile of the bf16-rounded D (bf16 D only); NULL to skip.
  *   cta_group: 1, 2 (CTA-pair MMA, 256x256 tiles) or 0 = library default.
@@ -80,6 +81,7 @@ typedef struct ClearGemmArgs {
   int32_t d_f32, accumulate;
   int32_t cta_group;
   int32_t raster_m_fast; /* 1: walk M first (default for forward), 0: walk N first, -1: auto */
+  int32_t k_splits;      /* 0/1: none; 2..4: split K over work items (needs d_f32 = accumulate = 1, D pre-zeroed) */
 } ClearGemmArgs;
 int clear_gemm_bf16(const ClearGemmArgs* args, void* stream);
 
@@ -148,7 +150,7 @@ int clear_head_reduce_sequences(const float* loss_rows, int64_t n_seqs, int64_t 
 /* ---------------------------------------------------------------------------------------------
  * Loss head, stage 3 — backward projections (autograd of nn.Linear, K9):
  *   dhidden[n_rows, hidden_dim] = dlogits * weight           (bf16 out; NULL to skip)
- *   dweight[vocab, hidden_dim]  = dlogits^T * hidden         (bf16, or fp32 with optional accumulate)
+ *   dweight[vocab, hidden_dim]  = dlogits^T * hidden         (bf16 or fp32; accumulate: += , bf16 rounds per add)
  * ------------------------------------------------------------------------------------------- */
 typedef struct ClearBackwardArgs {
   const void* dlogits; /* bf16 [n_rows, dlogits_ld] */
@@ -161,6 +163,10 @@ typedef struct ClearBackwardArgs {
   int32_t hidden_dim, vocab;
   int32_t dweight_f32, accumulate;
   int32_t cta_group;
+  /* optional fp32 [n_rows, hidden_dim] workspace (row stride hidden_dim): lets the library cut the dH contraction
+   * along the vocabulary (split-K, fp32 reduce-add, one conversion pass) when its output tiles alone would leave
+   * the last wave of SM pairs mostly idle.  NULL: never split. */
+  float* dhidden_ws;
 } ClearBackwardArgs;
 int clear_head_backward(const ClearBackwardArgs* args, void* stream);
 

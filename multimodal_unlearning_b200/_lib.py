@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
                 ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
                 ("a_major", C.c_int32), ("b_major", C.c_int32),
                 ("d_f32", C.c_int32), ("accumulate", C.c_int32),
-                ("cta_group", C.c_int32), ("raster_m_fast", C.c_int32)]
+                ("cta_group", C.c_int32), ("raster_m_fast", C.c_int32), ("k_splits", C.c_int32)]
 
 
 class ProjectArgs(C.Structure):
@@ -53,7 +53,7 @@ class BackwardArgs(C.Structure):
                 ("dlogits_ld", C.c_int64), ("hidden_ld", C.c_int64), ("weight_ld", C.c_int64),
                 ("dhidden_ld", C.c_int64), ("dweight_ld", C.c_int64), ("n_rows", C.c_int64),
                 ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("dweight_f32", C.c_int32),
-                ("accumulate", C.c_int32), ("cta_group", C.c_int32)]
+                ("accumulate", C.c_int32), ("cta_group", C.c_int32), ("dhidden_ws", C.c_void_p)]
 
 
 class AdamWArgs(C.Structure):

@@ -36,6 +36,8 @@ struct GemmOperand {
   int major;   // 0: K-major  (storage [MN, K]);  1: MN-major (storage [K, MN])
 };
 int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
-                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream);
+                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits = 1);
+// Number of K splits (1..4) that best fills the last wave of CTA groups for this problem.
+int gemm_pick_k_splits(int cta_group, int m, int n, int k);
 
 }  // namespace clear

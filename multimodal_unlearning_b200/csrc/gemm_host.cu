@@ -104,7 +104,7 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   const int sms = device_sm_count();
   if (sms <= 0) return fail(CLEAR_ERR_DEVICE, "cannot query SM count");
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
   int groups = sms / kCtaGroup;
   if (groups > tiles) groups = tiles;
   cudaLaunchConfig_t cfg = {};
@@ -123,8 +123,26 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return 0;
 }
 
+int gemm_pick_k_splits(int cta_group, int m, int n, int k) {
+  if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
+  const int sms = device_sm_count();
+  if (sms <= 0) return 1;
+  const int groups = sms / cta_group;
+  const int tiles = ((m + 128 * cta_group - 1) / (128 * cta_group)) * ((n + 255) / 256);
+  const int num_kb = (k + 63) / 64;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 4; ++s) {
+    if (s > 1 && num_kb / s < 64) break;  // keep >= 4096 of K per item: the fp32 epilogue must stay hidden
+    const double waves = (double)tiles * s / groups;
+    const double eff = waves / (double)(long long)(waves + 0.999999);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = s; }  // a split must buy at least 3 % to be worth the fp32 pass
+  }
+  return best;
+}
+
 int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
-                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream) {
+                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits) {
   if (!a.ptr || !b.ptr || !d) return fail(CLEAR_ERR_NULL, "gemm: null operand");
   if (m <= 0 || n <= 0 || k <= 0) return fail(CLEAR_ERR_SHAPE, "gemm: non-positive dims m=%d n=%d k=%d", m, n, k);
   if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
@@ -140,7 +158,9 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
   if (b.major == kMajorK && b.ld < k) return fail(CLEAR_ERR_SHAPE, "gemm: ldb < k");
   if (ldd < n) return fail(CLEAR_ERR_SHAPE, "gemm: ldd < n");
   if (lse_part && d_is_f32) return fail(CLEAR_ERR_KIND, "gemm: lse_part requires a bf16 output");
-  if (reduce_add && !d_is_f32) return fail(CLEAR_ERR_KIND, "gemm: accumulate requires an fp32 output");
+  if (reduce_add && lse_part) return fail(CLEAR_ERR_KIND, "gemm: accumulate cannot be combined with lse_part");
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > 1 && !reduce_add) return fail(CLEAR_ERR_KIND, "gemm: split-K requires the reduce-add epilogue (accumulate = 1)");
 
   CUtensorMap tmA, tmB, tmD;
   int rc;
@@ -154,6 +174,13 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
   p.n_tiles = (n + 255) / 256;
   p.raster_m_fast = raster_m_fast;
   p.reduce_add = reduce_add;
+  {
+    const int num_kb = (k + 63) / 64;
+    if (k_splits > num_kb) k_splits = num_kb;
+    p.k_splits = k_splits;
+    p.kb_per_split = (num_kb + k_splits - 1) / k_splits;
+    p.k_splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty item
+  }
   p.lse_part = reinterpret_cast<float2*>(lse_part);
 
   const int epi = d_is_f32 ? kEpiStoreF32 : (lse_part ? kEpiStoreBF16Lse : kEpiStoreBF16);
@@ -163,11 +190,13 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
   CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16)
   CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16Lse)
   CLEAR_DISPATCH(1, kMajorK, kMajorMN, kEpiStoreBF16)
+  CLEAR_DISPATCH(1, kMajorK, kMajorMN, kEpiStoreF32)
   CLEAR_DISPATCH(1, kMajorMN, kMajorMN, kEpiStoreBF16)
   CLEAR_DISPATCH(1, kMajorMN, kMajorMN, kEpiStoreF32)
   CLEAR_DISPATCH(2, kMajorK, kMajorK, kEpiStoreBF16)
   CLEAR_DISPATCH(2, kMajorK, kMajorK, kEpiStoreBF16Lse)
   CLEAR_DISPATCH(2, kMajorK, kMajorMN, kEpiStoreBF16)
+  CLEAR_DISPATCH(2, kMajorK, kMajorMN, kEpiStoreF32)
   CLEAR_DISPATCH(2, kMajorMN, kMajorMN, kEpiStoreBF16)
   CLEAR_DISPATCH(2, kMajorMN, kMajorMN, kEpiStoreF32)
 #undef CLEAR_DISPATCH
@@ -202,7 +231,7 @@ int clear_gemm_bf16(const ClearGemmArgs* g, void* stream) {
   int raster = g->raster_m_fast;
   if (raster < 0) raster = (int64_t)g->m <= (int64_t)g->n ? 1 : 0;
   return clear::launch_gemm_bf16(g->cta_group, a, b, g->d, g->d_f32, g->ldd, g->m, g->n, g->k, g->lse_part,
-                                 g->accumulate, raster, static_cast<cudaStream_t>(stream));
+                                 g->accumulate, raster, static_cast<cudaStream_t>(stream), g->k_splits);
 }
 
 }  // extern "C"

@@ -30,7 +30,9 @@ struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles;  // in units of (128*cta_group) x 256
   int raster_m_fast;     // 1: consecutive tiles walk M first (A small / re-read from L2), 0: N first
-  int reduce_add;        // fp32 epilogue only: accumulate into D instead of overwriting
+  int reduce_add;        // accumulate into D instead of overwriting (TMA reduce-add; bf16 D rounds after each add)
+  int k_splits;          // > 1: each output tile is cut into k_splits work items along K (fp32 reduce-add epilogue)
+  int kb_per_split;      // K blocks (of 64) per work item
   float2* lse_part;      // [M][n_tiles] when kEpiStoreBF16Lse
 };
 
@@ -126,21 +128,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // Work item w = (output tile, K split): consecutive items are the splits of one tile.
+  const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int tile_stride = gridDim.x / kCtaGroup;
   const int tile_first = blockIdx.x / kCtaGroup;
-  const int num_kb = (p.K + S::BK - 1) / S::BK;
+  const int num_kb_total = (p.K + S::BK - 1) / S::BK;
 
   if (warp == 0) {
     // ===================================== TMA producer ==========================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = tile_first; t < num_tiles; t += tile_stride) {
+      for (int w = tile_first; w < num_tiles; w += tile_stride) {
+        const int t = w / p.k_splits;
+        const int kb0 = (w % p.k_splits) * p.kb_per_split;
+        const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         const int mt = p.raster_m_fast ? (t % p.m_tiles) : (t / p.n_tiles);
         const int nt = p.raster_m_fast ? (t / p.m_tiles) : (t % p.n_tiles);
         const int m0 = (mt * kCtaGroup + (int)cta_rank) * S::BM;
         const int n0 = nt * S::BN + (int)cta_rank * S::B_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar + stage * 8, phase ^ 1u);
           const uint32_t fb = full_bar + stage * 8;
           if (cta_rank == 0) ptx::mbar_arrive_expect_tx(fb, S::STAGE_BYTES * kCtaGroup);
@@ -177,11 +183,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t a_lbo = (kMajorA == kMajorK) ? 16u : (S::BK * 128);
       constexpr uint32_t b_lbo = (kMajorB == kMajorK) ? 16u : (S::BK * 128);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int t = tile_first; t < num_tiles; t += tile_stride) {
+      for (int w = tile_first; w < num_tiles; w += tile_stride) {
+        const int kb0 = (w % p.k_splits) * p.kb_per_split;
+        const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         ptx::mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * S::BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(full_bar + stage * 8, phase);
           ptx::tcgen05_fence_after();
           const uint32_t a_src = smem_base + stage * S::STAGE_BYTES;
@@ -191,7 +199,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < S::BK / S::UMMA_K; ++k) {
             ptx::umma_f16<kCtaGroup>(d_tmem, adesc + ((k * a_adv) >> 4), bdesc + ((k * b_adv) >> 4), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                                     ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit<kCtaGroup>(empty_bar + stage * 8);  // frees the smem slot once the MMAs retire
           if (++stage == S::STAGES) { stage = 0; phase ^= 1u; }
@@ -207,7 +215,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t stg = epi_addr + q * S::EPI_WARP_BYTES;
     const uint32_t sw = (lane & 7u);
     uint32_t nstores = 0, acc = 0, acc_phase = 0;
-    for (int t = tile_first; t < num_tiles; t += tile_stride) {
+    for (int w = tile_first; w < num_tiles; w += tile_stride) {
+      const int t = w / p.k_splits;
       const int mt = p.raster_m_fast ? (t % p.m_tiles) : (t / p.n_tiles);
       const int nt = p.raster_m_fast ? (t / p.m_tiles) : (t % p.n_tiles);
       const int row0 = (mt * kCtaGroup + (int)cta_rank) * S::BM + (int)q * 32;
@@ -285,7 +294,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::st_shared_v4(rowp + (((uint32_t)j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && col0 + c * 64 < p.N) ptx::tma_store_2d(&tmD, buf, col0 + c * 64, row0);
+          if (lane == 0 && row0 < p.M && col0 + c * 64 < p.N) {
+            if (p.reduce_add) ptx::tma_reduce_add_2d(&tmD, buf, col0 + c * 64, row0);  // bf16 += (rounded in L2)
+            else              ptx::tma_store_2d(&tmD, buf, col0 + c * 64, row0);
+          }
           if (lane == 0) ptx::tma_store_commit();
           ++nstores;
         }

@@ -149,23 +149,33 @@ __global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossPa
   const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
   const float lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
   const float lse_t = merge_lse(a.ref_lse_part + row * a.n_vtiles, a.n_vtiles);
+  const float nls2 = -lse_s * kLog2e, nlt2 = -lse_t * kLog2e, dlse = lse_s - lse_t;
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
   const int nvec = (int)(a.ld >> 3);
+  const int nfull = a.vocab >> 3;
   const int ref_nvec = (int)(a.ref_ld >> 3);  // a materialised teacher may be narrower than the staging buffer
   float acc = 0.f;
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(z)[v], x);
     unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
-    const int c0 = v << 3;
+    if (v < nfull) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const bool in = (c0 + j < a.vocab);
-      const float lp = x[j] - lse_s, lq = r[j] - lse_t;
-      const float p = ptx::ex2_approx(lp * kLog2e), q = ptx::ex2_approx(lq * kLog2e);
-      if (in) acc += q * (lq - lp);
-      x[j] = in ? g * (p - q) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const float p = ptx::ex2_approx(fmaf(x[j], kLog2e, nls2)), q = ptx::ex2_approx(fmaf(r[j], kLog2e, nlt2));
+        acc = fmaf(q, (r[j] - x[j]) + dlse, acc);  // q (lq - lp)
+        x[j] = g * (p - q);
+      }
+    } else {
+      const int c0 = v << 3;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool in = (c0 + j < a.vocab);
+        const float p = ptx::ex2_approx(fmaf(x[j], kLog2e, nls2)), q = ptx::ex2_approx(fmaf(r[j], kLog2e, nlt2));
+        if (in) acc = fmaf(q, (r[j] - x[j]) + dlse, acc);
+        x[j] = in ? g * (p - q) : 0.f;
+      }
     }
     if (a.write_grad) reinterpret_cast<uint4*>(z)[v] = pack8(x);
   }
@@ -179,48 +189,50 @@ __global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossPa
 //   NPO    : S = sum s, s = t/(1+t), t = (p/(q+1e-8))^beta; loss = sum log(1+t);
 //            dz = g (s - p S)                                                          (A6)
 //   ENTROPY: E = sum p lp;                   dz = g p (lp - E)                         (A6b)
-// The second pass re-reads the row (it was just streamed by this CTA: an L2 hit).
+// The second pass re-reads the row (it was just streamed by this CTA: an L2 hit).  NPO is bound by the XU
+// (MUFU) pipe, not by HBM: 7 transcendental ops per logit over the two passes, so everything around them
+// is kept to a minimum — exponent arguments are one FFMA (constants pre-scaled by log2 e), the loss is
+// accumulated in log2 units, and the vocabulary bound is tested only in the row's last (ragged) vectors.
 // ---------------------------------------------------------------------------------------------------
+struct RowConsts {
+  float nls2, nlt2;  // -lse * log2(e) of student / teacher
+  float dlse;        // lse_t - lse_s
+  float lse_s;
+  float beta;
+};
+
 template <int kKind, bool kBetaOne>
 struct RowTerm {
-  // returns (stat contribution, loss contribution); p, aux are kept for pass 2
-  __device__ static __forceinline__ void eval(float x, float r, float lse_s, float lse_t, float beta, float& p,
-                                              float& aux, float& stat, float& loss) {
-    const float lp = x - lse_s;
-    p = ptx::ex2_approx(lp * kLog2e);
+  // One logit: p and the auxiliary term pass 2 needs; adds to the row statistic and to the loss (log2 units for NPO).
+  __device__ static __forceinline__ void eval(float x, float r, const RowConsts& c, float& p, float& aux, float& stat,
+                                              float& loss) {
+    p = ptx::ex2_approx(fmaf(x, kLog2e, c.nls2));
     if constexpr (kKind == CLEAR_KIND_KL_REV) {
-      const float d = lp - (r - lse_t);
-      aux = d;
-      stat = p * d;
-      loss = stat;
+      aux = (x - r) + c.dlse;  // lp - lq
+      stat = fmaf(p, aux, stat);
     } else if constexpr (kKind == CLEAR_KIND_ENTROPY) {
-      aux = lp;
-      stat = p * lp;  // p == 0 gives 0 (the reference's fp32 softmax would give 0 * -inf = NaN; App. B #10)
-      loss = stat;
+      aux = x - c.lse_s;       // lp
+      stat = fmaf(p, aux, stat);  // p == 0 gives 0 (the reference's fp32 softmax would give 0 * -inf = NaN; App. B #10)
     } else {  // NPO
-      const float q = ptx::ex2_approx((r - lse_t) * kLog2e);
+      const float q = ptx::ex2_approx(fmaf(r, kLog2e, c.nlt2));
       const float A = q + 1e-8f;
-      float t, inv1pt;
       if constexpr (kBetaOne) {
-        const float B = p + A;
-        const float invB = ptx::rcp_approx(B);
-        aux = p * invB;                                   // s = t / (1 + t) = p / (p + q + eps)
-        loss = -ptx::lg2_approx(A * invB) * kLn2;         // log(1 + t) = -log(1 - s)
-        (void)t; (void)inv1pt;
+        const float invB = ptx::rcp_approx(p + A);
+        aux = p * invB;                          // s = t / (1 + t) = p / (p + q + eps)
+        loss -= ptx::lg2_approx(A * invB);       // log2(1 + t) = -log2(1 - s)
       } else {
-        const float ratio = p * ptx::rcp_approx(A);
-        t = ptx::ex2_approx(beta * ptx::lg2_approx(ratio));
+        const float t = ptx::ex2_approx(c.beta * ptx::lg2_approx(p * ptx::rcp_approx(A)));
         const float opt = 1.f + t;
-        inv1pt = ptx::rcp_approx(opt);
-        aux = t * inv1pt;
-        loss = ptx::lg2_approx(opt) * kLn2;
+        aux = t * ptx::rcp_approx(opt);
+        loss += ptx::lg2_approx(opt);
       }
-      stat = aux;
+      stat += aux;
     }
   }
-  __device__ static __forceinline__ float grad(float p, float aux, float stat_total) {
-    if constexpr (kKind == CLEAR_KIND_NPO) return aux - p * stat_total;
-    else return p * (aux - stat_total);
+  // gscale = g (KL_REV, ENTROPY) ; for NPO the caller passes g and gS = g * S
+  __device__ static __forceinline__ float grad(float p, float aux, float g, float gstat) {
+    if constexpr (kKind == CLEAR_KIND_NPO) return fmaf(-p, gstat, g * aux);   // g (s - p S)
+    else return (g * p) * (aux - gstat);                                      // gstat = K or E (unscaled)
   }
 };
 
@@ -231,40 +243,68 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
   const __nv_bfloat16* zr = kNeedsRef ? a.ref_logits + row * a.ref_ld : nullptr;
-  const float lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
+  RowConsts c;
+  c.lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
   const float lse_t = kNeedsRef ? merge_lse(a.ref_lse_part + row * a.n_vtiles, a.n_vtiles) : 0.f;
+  c.nls2 = -c.lse_s * kLog2e;
+  c.nlt2 = -lse_t * kLog2e;
+  c.dlse = lse_t - c.lse_s;
+  c.beta = a.beta;
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
   const int nvec = (int)(a.ld >> 3);
+  const int nfull = a.vocab >> 3;  // vectors entirely inside the vocabulary (the teacher row covers them: ref_ld >= vocab)
   const int ref_nvec = kNeedsRef ? (int)(a.ref_ld >> 3) : 0;
   float stat = 0.f, loss = 0.f;
-  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+  for (int v = threadIdx.x; v < nfull; v += kThreads) {
     float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-    if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
-    const int c0 = v << 3;
+    if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float p, aux, st, ls;
-      RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, lse_s, lse_t, a.beta, p, aux, st, ls);
-      if (c0 + j < a.vocab) { stat += st; loss += ls; }
+      float p, aux;
+      RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, c, p, aux, stat, loss);
+    }
+  }
+  {  // ragged tail: at most one partially valid vector
+    const int v = nfull + threadIdx.x;
+    if (threadIdx.x == 0 && (a.vocab & 7)) {
+      float x[8], r[8];
+      unpack8(reinterpret_cast<const uint4*>(z)[v], x);
+      if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
+      for (int j = 0; j < (a.vocab & 7); ++j) {
+        float p, aux;
+        RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, c, p, aux, stat, loss);
+      }
     }
   }
   stat = block_sum<kThreads>(stat, red);
-  if constexpr (kKind == CLEAR_KIND_NPO) loss = block_sum<kThreads>(loss, red);
+  if constexpr (kKind == CLEAR_KIND_NPO) loss = block_sum<kThreads>(loss, red) * kLn2;
   else loss = stat;
   if (threadIdx.x == 0) a.loss_rows[row] = loss * w;
   if (!a.write_grad) return;
+  const float gstat = (kKind == CLEAR_KIND_NPO) ? g * stat : stat;
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8], r[8];
-    unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-    if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
-    const int c0 = v << 3;
+    if (v < nfull) {
+      unpack8(reinterpret_cast<const uint4*>(z)[v], x);
+      if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float p, aux, st, ls;
-      RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, lse_s, lse_t, a.beta, p, aux, st, ls);
-      x[j] = (c0 + j < a.vocab) ? g * RowTerm<kKind, kBetaOne>::grad(p, aux, stat) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        float p, aux, st = 0.f, ls = 0.f;
+        RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, c, p, aux, st, ls);
+        x[j] = RowTerm<kKind, kBetaOne>::grad(p, aux, g, gstat);
+      }
+    } else {  // ragged / padding vectors
+      unpack8(reinterpret_cast<const uint4*>(z)[v], x);
+      if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
+      const int c0 = v << 3;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p, aux, st = 0.f, ls = 0.f;
+        RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, c, p, aux, st, ls);
+        x[j] = (c0 + j < a.vocab) ? RowTerm<kKind, kBetaOne>::grad(p, aux, g, gstat) : 0.f;
+      }
     }
     reinterpret_cast<uint4*>(z)[v] = pack8(x);
   }
@@ -297,6 +337,20 @@ __global__ void __launch_bounds__(256) lse_partials_kernel(const __nv_bfloat16* 
     s = warp_sum(s);
     if (lane == 0) part[row * n_vtiles + t] = make_float2(m, s);
   }
+}
+
+// fp32 [rows, cols] (dense) -> bf16 [rows, ld]: the conversion pass after a split-K dH contraction.
+__global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* src, __nv_bfloat16* dst, int cols, int64_t ld,
+                                                               int64_t nvec) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= nvec) return;
+  const int vec_per_row = cols >> 3;
+  const int64_t row = i / vec_per_row;
+  const int c = (int)(i - row * vec_per_row) << 3;
+  const float4 a = *reinterpret_cast<const float4*>(src + row * cols + c);
+  const float4 b = *reinterpret_cast<const float4*>(src + row * cols + c + 4);
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  *reinterpret_cast<uint4*>(dst + row * ld + c) = pack8(x);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -465,13 +519,25 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
     // dH[n, h] = sum_v dZ[n, v] W[v, h]: A = dZ (K-major, K = vocab), B = W read MN-major.
     GemmOperand A{a->dlogits, a->dlogits_ld, kMajorK};
     GemmOperand B{a->weight, a->weight_ld, kMajorMN};
-    rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden, 0, a->dhidden_ld, (int)a->n_rows, a->hidden_dim, a->vocab,
-                          nullptr, 0, /*raster_m_fast=*/0, stream);
-    if (rc) return rc;
+    const int splits = a->dhidden_ws ? gemm_pick_k_splits(a->cta_group, (int)a->n_rows, a->hidden_dim, a->vocab) : 1;
+    if (splits > 1) {
+      const size_t ws_elems = (size_t)a->n_rows * a->hidden_dim;
+      CLEAR_CUDA_OK(cudaMemsetAsync(a->dhidden_ws, 0, ws_elems * sizeof(float), stream));
+      rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden_ws, 1, a->hidden_dim, (int)a->n_rows, a->hidden_dim, a->vocab,
+                            nullptr, /*reduce_add=*/1, /*raster_m_fast=*/0, stream, splits);
+      if (rc) return rc;
+      const int64_t nvec = (int64_t)a->n_rows * (a->hidden_dim / 8);
+      f32_to_bf16_rows_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, stream>>>(
+          a->dhidden_ws, static_cast<__nv_bfloat16*>(a->dhidden), a->hidden_dim, a->dhidden_ld, nvec);
+      CLEAR_CUDA_OK(cudaGetLastError());
+    } else {
+      rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden, 0, a->dhidden_ld, (int)a->n_rows, a->hidden_dim, a->vocab,
+                            nullptr, 0, /*raster_m_fast=*/0, stream);
+      if (rc) return rc;
+    }
   }
   if (a->dweight) {
     if (!a->hidden) return fail(CLEAR_ERR_NULL, "clear_head_backward: dweight requested but hidden is NULL");
-    if (a->accumulate && !a->dweight_f32) return fail(CLEAR_ERR_KIND, "clear_head_backward: accumulate needs fp32 dweight");
     // dW[v, h] = sum_n dZ[n, v] H[n, h]: both operands read MN-major (K = rows).
     GemmOperand A{a->dlogits, a->dlogits_ld, kMajorMN};
     GemmOperand B{a->hidden, a->hidden_ld, kMajorMN};

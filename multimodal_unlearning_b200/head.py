@@ -30,9 +30,13 @@ IGNORE_INDEX = -100
 KIND_NAMES = {KIND_CE: "ce", KIND_KL_FWD: "kl_fwd", KIND_KL_REV: "kl_rev", KIND_NPO: "npo", KIND_ENTROPY: "entropy"}
 _NEEDS_REF = (KIND_KL_FWD, KIND_KL_REV, KIND_NPO)
 
-# Rows staged per pass.  4096 rows x 32064 bf16 = 263 MB per operand: large enough that the dW
-# contraction (K = block_rows) runs near its peak, small against 180 GB.
-DEFAULT_BLOCK_ROWS = 4096
+# Rows staged per pass.  8192 rows x 32064 bf16 = 525 MB per projected operand, small against 180 GB of HBM3e.
+# Measured on B200 under the 1 kW power cap (tools/gpu_probe2.py, interleaved A/B, NPO step at N = 8192):
+# 8192-row blocks 7.13 ms, 4096-row blocks 7.42 ms (7.20 ms with the two-stream overlap), 2048-row blocks 8.30 ms —
+# fewer blocks mean fewer read-modify-write passes over dW and fuller waves of output tiles in the dH contraction.
+DEFAULT_BLOCK_ROWS = 8192
+# Up to this many row blocks accumulate dW directly in bf16; beyond it an fp32 accumulator is used and converted once.
+MAX_BF16_ACCUM_BLOCKS = 4
 
 
 def _stream() -> C.c_void_p:
@@ -136,7 +140,7 @@ def rowloss(kind: int, logits: torch.Tensor, lse_part: torch.Tensor, loss_rows: 
 
 def backward(dlogits: torch.Tensor, vocab: int, hidden: torch.Tensor, weight: torch.Tensor,
              dhidden: torch.Tensor | None, dweight: torch.Tensor | None, accumulate: bool = False,
-             cta_group: int = 0) -> None:
+             cta_group: int = 0, dhidden_ws: torch.Tensor | None = None) -> None:
     lib = _lib.load()
     a = _lib.BackwardArgs(dlogits=dlogits.data_ptr(), hidden=hidden.data_ptr(), weight=weight.data_ptr(),
                           dhidden=_ptr(dhidden), dweight=_ptr(dweight), dlogits_ld=dlogits.stride(0),
@@ -145,7 +149,7 @@ def backward(dlogits: torch.Tensor, vocab: int, hidden: torch.Tensor, weight: to
                           dweight_ld=dweight.stride(0) if dweight is not None else 0, n_rows=dlogits.shape[0],
                           hidden_dim=hidden.shape[1], vocab=vocab,
                           dweight_f32=int(dweight is not None and dweight.dtype == torch.float32),
-                          accumulate=int(accumulate), cta_group=cta_group)
+                          accumulate=int(accumulate), cta_group=cta_group, dhidden_ws=_ptr(dhidden_ws))
     if StageTimer.active is None or dhidden is None or dweight is None:
         tag = "gemm_dweight" if dhidden is None else ("gemm_dhidden" if dweight is None else "gemm_backward")
         _timed(tag, lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
@@ -303,10 +307,15 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
             if dweight_accum.dtype != torch.float32 or dweight_accum.shape != weight.shape or not dweight_accum.is_contiguous():
                 raise RuntimeError("dweight_accum must be a contiguous fp32 [V, H] tensor")
             dweight = dweight_accum
-        elif n_blocks == 1:
-            dweight = torch.empty_like(weight)          # single block: bf16 straight from the epilogue
+        elif n_blocks <= MAX_BF16_ACCUM_BLOCKS:
+            # bf16 straight from the epilogue; later blocks are added by TMA reduce-add, rounded to bf16 per add —
+            # the precision of torch's own bf16 gradient accumulation across micro-batches
+            dweight = torch.empty_like(weight)
         else:
             dweight = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+
+    # fp32 scratch for a split-K dH contraction (used only when the library finds the plain one wave-starved)
+    dh_ws = torch.empty((blk, h), dtype=torch.float32, device=dev) if need_dhidden and h % 8 == 0 else None
 
     def block(b):
         r0, r1 = b * blk, min(n, (b + 1) * blk)
@@ -337,7 +346,8 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     def do_backward(b):
         r0, r1, zb, _ = block(b)
         backward(zb, v, hidden[r0:r1], weight, dhidden[r0:r1] if need_dhidden else None,
-                 dweight if need_dweight else None, accumulate=(dweight_accum is not None) or b > 0, cta_group=cta_group)
+                 dweight if need_dweight else None, accumulate=(dweight_accum is not None) or b > 0, cta_group=cta_group,
+                 dhidden_ws=dh_ws)
 
     launches += n_blocks * (2 + int(needs_ref) + (int(need_dhidden) + int(need_dweight) if write_grad else 0))
     if not pipelined:

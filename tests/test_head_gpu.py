@@ -419,3 +419,38 @@ def test_baseline_size_parity(kind, n, h, v):
     scale = (1.0 / (y != -100).sum().item()) if kind == HO.KIND_CE else 2.0 / (n * v)
     want_rows_dh = (dterm * scale) @ w.double().cpu()
     assert _rel(res.dhidden[idx.to(dev)], want_rows_dh) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("k_splits", [1, 2, 3])
+@pytest.mark.parametrize("layout", ["k_mn", "mn_mn"])
+def test_gemm_split_k_reduce_add(k_splits, layout):
+    """clear_gemm_bf16 with the fp32 reduce-add epilogue and K cut into work items (the dH / dW operand layouts)."""
+    import ctypes as C
+
+    from multimodal_unlearning_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    m, n, k = 384, 520, 1000
+    g = torch.Generator().manual_seed(40 + k_splits)
+    A = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    B = torch.randn(n, k, generator=g).to(torch.bfloat16)
+    pad = lambda x: (x + 63) // 64 * 64
+    if layout == "k_mn":   # A stored [m, k], B stored [k, n]
+        a_st = torch.zeros(m, pad(k), dtype=torch.bfloat16); a_st[:, :k] = A
+        b_st = torch.zeros(k, pad(n), dtype=torch.bfloat16); b_st[:, :n] = B.t()
+        a_major, b_major = 0, 1
+    else:                  # A stored [k, m], B stored [k, n]
+        a_st = torch.zeros(k, pad(m), dtype=torch.bfloat16); a_st[:, :m] = A.t()
+        b_st = torch.zeros(k, pad(n), dtype=torch.bfloat16); b_st[:, :n] = B.t()
+        a_major, b_major = 1, 1
+    a_st, b_st = a_st.to(dev), b_st.to(dev)
+    D = torch.full((m, pad(n)), 0.5, dtype=torch.float32, device=dev)   # accumulate on top of existing contents
+    args = _lib.GemmArgs(a=a_st.data_ptr(), b=b_st.data_ptr(), d=D.data_ptr(), lse_part=None, lda=a_st.stride(0),
+                         ldb=b_st.stride(0), ldd=D.stride(0), m=m, n=n, k=k, a_major=a_major, b_major=b_major, d_f32=1,
+                         accumulate=1, cta_group=0, raster_m_fast=-1, k_splits=k_splits)
+    _lib.check(lib.clear_gemm_bf16(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "clear_gemm_bf16")
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().t() + 0.5
+    got = D[:, :n].cpu()
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+    assert (D[:, n:] == 0.5).all()
