@@ -215,8 +215,32 @@ typedef struct ClearAdamWArgs {
   int64_t n;
   double lr, beta1, beta2, eps, weight_decay; /* doubles: the scalar prologue runs in double like torch's */
   int32_t step;
+  const float* grad_scale_dev; /* optional device scalar (gradient-clipping coefficient): g = bf16(g * scale) first,
+                                  like torch's in-place `grad.mul_(clip_coef)` on a bf16 gradient */
 } ClearAdamWArgs;
 int clear_masked_adamw(const ClearAdamWArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-model reductions around the update (one pass over HBM each, bitwise reproducible).
+ * partials: double workspace of clear_reduce_partials_elems() elements; out: device doubles;
+ * accumulate != 0 adds to *out (tensor-by-tensor use), else overwrites.
+ *   clear_grad_sqnorm: out[0] (+)= sum (grad * mask)^2       — torch.nn.utils.clip_grad_norm_ (HF Trainer's
+ *                      default max_grad_norm = 1.0; the override is commented out at mm/forget.py:151)
+ *   clear_clip_coef:   coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))
+ *   clear_param_l1l0:  out[0] (+)= sum |p - ref|, out[1] (+)= #{p != ref}; ref NULL = zeros
+ *                      — torch.norm(torch.cat(params), p=1 / p=0), mm/trainer.py:451-481 (A9)
+ * ------------------------------------------------------------------------------------------- */
+int64_t clear_reduce_partials_elems(void);
+int clear_grad_sqnorm(const void* grad, const int8_t* mask, int64_t n, double* partials, double* out, int accumulate,
+                      void* stream);
+int clear_clip_coef(const double* sumsq, double max_norm, float* coef, void* stream);
+/* grad[i] = bf16(grad[i] * *coef) in place (torch: grads.mul_(clip_coef_clamped)); the fused alternative is
+ * ClearAdamWArgs.grad_scale_dev */
+int clear_grad_scale(void* grad, int64_t n, const float* coef, void* stream);
+int clear_param_l1l0(const void* param, const void* ref, int64_t n, double* partials, double* out2, int accumulate,
+                     void* stream);
+/* out[i] = bf16(*coef * sign(param[i] - ref[i])): backward of coef * ||param - ref||_1 (the L0 term has zero gradient) */
+int clear_param_l1_grad(const void* param, const void* ref, int64_t n, const float* coef, void* out, void* stream);
 
 #ifdef __cplusplus
 }

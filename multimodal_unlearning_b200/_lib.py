@@ -19,7 +19,8 @@ EXPORTED_SYMBOLS = (
     "clear_head_project", "clear_head_lse_partials", "clear_head_rowloss", "clear_head_count_valid", "clear_head_reduce_rows",
     "clear_head_reduce_sequences", "clear_head_backward", "clear_saliency_accumulate",
     "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_chunk_elems", "clear_saliency_mask",
-    "clear_masked_adamw",
+    "clear_masked_adamw", "clear_reduce_partials_elems", "clear_grad_sqnorm", "clear_clip_coef", "clear_param_l1l0",
+    "clear_param_l1_grad", "clear_grad_scale",
 )
 
 
@@ -60,7 +61,7 @@ class AdamWArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("mask", C.c_void_p), ("n", C.c_int64),
                 ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
-                ("weight_decay", C.c_double), ("step", C.c_int32)]
+                ("weight_decay", C.c_double), ("step", C.c_int32), ("grad_scale_dev", C.c_void_p)]
 
 
 _lib = None
@@ -97,6 +98,13 @@ def load() -> C.CDLL:
     lib.clear_saliency_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.clear_masked_adamw.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]
+    lib.clear_reduce_partials_elems.argtypes = []
+    lib.clear_reduce_partials_elems.restype = C.c_int64
+    lib.clear_grad_sqnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.clear_clip_coef.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    lib.clear_param_l1l0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.clear_param_l1_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.clear_grad_scale.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError here = the .so is stale / does not match include/clear_b200.h
     if lib.clear_abi_version() != 1:

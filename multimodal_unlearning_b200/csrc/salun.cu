@@ -484,6 +484,7 @@ struct AdamConsts {
   float bc2_sqrt;   // sqrt(1 - beta2^step)
   float step_size;  // lr / (1 - beta1^step)
   float eps;
+  const float* grad_scale;  // optional device scalar: clipping coefficient
 };
 
 __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamConsts& c) {
@@ -506,6 +507,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
                                                     float* exp_avg_sq, const int8_t* mask, int64_t n, AdamConsts c) {
   const int64_t nvec = n >> 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float gscale = c.grad_scale ? *c.grad_scale : 1.f;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kAdamVecs) {
     uint4 pr[kAdamVecs], gr[kAdamVecs];
     float4 m0[kAdamVecs], m1[kAdamVecs], v0[kAdamVecs], v1[kAdamVecs];
@@ -534,7 +536,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t mb = ((j < 4 ? mk[u].x : mk[u].y) >> (8 * (j & 3))) & 0xFFu;
-        const float g = mb ? __bfloat162float(gh[j]) : 0.f;  // grad *= mask
+        float g = mb ? __bfloat162float(gh[j]) : 0.f;  // grad *= mask
+        if (c.grad_scale) g = __bfloat162float(__float2bfloat16_rn(__fmul_rn(g, gscale)));  // grad.mul_(clip_coef) in bf16
         ph[j] = __float2bfloat16_rn(adam_one(__bfloat162float(ph[j]), g, mm[j], vv[j], c));
       }
       reinterpret_cast<uint4*>(param)[i] = pr[u];
@@ -546,7 +549,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int64_t i = nvec << 3; i < n; ++i) {
-      const float g = (!mask || mask[i]) ? __bfloat162float(grad[i]) : 0.f;
+      float g = (!mask || mask[i]) ? __bfloat162float(grad[i]) : 0.f;
+      if (c.grad_scale) g = __bfloat162float(__float2bfloat16_rn(__fmul_rn(g, gscale)));
       param[i] = __float2bfloat16_rn(adam_one(__bfloat162float(param[i]), g, exp_avg[i], exp_avg_sq[i], c));
     }
   }
@@ -653,6 +657,7 @@ int clear_masked_adamw(const ClearAdamWArgs* a, void* stream) {
   c.step_size = (float)(a->lr / bc1);
   c.bc2_sqrt = (float)sqrt(bc2);
   c.eps = (float)a->eps;
+  c.grad_scale = a->grad_scale_dev;
   adamw_kernel<<<stream_grid(a->n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__nv_bfloat16*>(a->param), static_cast<const __nv_bfloat16*>(a->grad), a->exp_avg, a->exp_avg_sq,
       a->mask, a->n, c);

@@ -162,9 +162,15 @@ class MaskedAdamW(torch.optim.Optimizer):
     before `optimizer.step()`).  bf16 parameters and gradients, fp32 moments, torch's
     `_single_tensor_adam` operation order; one fused pass over 23 bytes per parameter."""
 
-    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, masks: dict | None = None):
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, masks: dict | None = None,
+                 max_grad_norm: float | None = None):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self.masks = masks or {}  # id(param) or param -> int8 tensor
+        self.masks = masks or {}  # param -> int8 tensor
+        # Global gradient-norm clipping fused into the update (HF Trainer's default max_grad_norm = 1.0 applies to
+        # the reference runs: the override is commented out at mm/forget.py:151).  The norm is taken over the MASKED
+        # gradients (what the update consumes); one extra 2-3 B/param pass, the coefficient never leaves the device.
+        self.max_grad_norm = max_grad_norm
+        self.last_grad_norm = None  # device fp64 [1] after a clipped step
 
     def set_mask(self, param: torch.Tensor, mask: torch.Tensor | None) -> None:
         if mask is None:
@@ -176,6 +182,14 @@ class MaskedAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         lib = _lib.load()
+        scale = None
+        if self.max_grad_norm is not None:
+            from . import norms
+            ps = [p for grp in self.param_groups for p in grp["params"] if p.grad is not None]
+            if ps:
+                sumsq = norms.grad_sqnorm([p.grad for p in ps], [self.masks.get(p) for p in ps])
+                scale = norms.clip_coef(sumsq, self.max_grad_norm)
+                self.last_grad_norm = sumsq.sqrt()
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -194,17 +208,19 @@ class MaskedAdamW(torch.optim.Optimizer):
                 a = _lib.AdamWArgs(param=p.data_ptr(), grad=g.data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
                                    exp_avg_sq=st["exp_avg_sq"].data_ptr(), mask=m.data_ptr() if m is not None else None,
                                    n=p.numel(), lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
-                                   weight_decay=group["weight_decay"], step=st["step"])
+                                   weight_decay=group["weight_decay"], step=st["step"],
+                                   grad_scale_dev=scale.data_ptr() if scale is not None else None)
                 _lib.check(lib.clear_masked_adamw(C.byref(a), _stream()), "clear_masked_adamw")
         return loss
 
 
 def masked_adamw_flat(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
                       mask: torch.Tensor | None, step: int, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
-                      weight_decay=0.01) -> None:
-    """One launch over a flat parameter buffer (the layout of FlatLayout)."""
+                      weight_decay=0.01, grad_scale: torch.Tensor | None = None) -> None:
+    """One launch over a flat parameter buffer (the layout of FlatLayout).  `grad_scale`: optional device fp32
+    scalar (norms.clip_coef) applied to the masked gradient first, rounded to bf16 like `grad.mul_(coef)`."""
     a = _lib.AdamWArgs(param=param.data_ptr(), grad=grad.data_ptr(), exp_avg=exp_avg.data_ptr(),
                        exp_avg_sq=exp_avg_sq.data_ptr(), mask=mask.data_ptr() if mask is not None else None,
                        n=param.numel(), lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
-                       step=step)
+                       step=step, grad_scale_dev=grad_scale.data_ptr() if grad_scale is not None else None)
     _lib.check(_lib.load().clear_masked_adamw(C.byref(a), _stream()), "clear_masked_adamw")

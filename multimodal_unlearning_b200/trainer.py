@@ -26,7 +26,7 @@ import contextlib
 import torch
 from torch import nn
 
-from . import head
+from . import head, norms
 from .head import KIND_CE, KIND_ENTROPY, KIND_KL_FWD, KIND_KL_REV, KIND_NPO
 
 try:  # transformers.Trainer needs `accelerate` to be *constructed*, not to be subclassed
@@ -238,23 +238,18 @@ def _regulariser(self, model, teacher, loss):
     l0 = getattr(self, "l0_lambda", None) or 0
     if l1 == 0 and l0 == 0:
         return loss
-    origin = getattr(self, "l_norm_from", "init" if teacher is not None and not has_lora_adapter(model) else "zero")
-    terms = []
+    origin = getattr(self, "l_norm_from", "init")  # the nlp trainer has no l_norm_from: always distance from the oracle
+    params = [p for p in model.parameters() if p.requires_grad]
+    refs = None
     if origin == "init" and not has_lora_adapter(model):
         if teacher is None:
             raise ValueError("Teacher model is required for L1/L0 regularization during training without LORA!")
-        for p, tp in zip(model.parameters(), teacher.parameters()):
-            if p.requires_grad:
-                terms.append(p - tp.to(p.device))
-    else:
-        if origin == "zero" and has_lora_adapter(model):
-            raise ValueError("L1/L0 regularization is not supported for LORA!")
-        terms = [p for p in model.parameters() if p.requires_grad]
-    if l1:
-        loss = loss + l1 * sum(t.float().abs().sum() for t in terms)
-    if l0:
-        loss = loss + l0 * sum((t != 0).sum() for t in terms).float()
-    return loss
+        refs = [tp.to(p.device) for p, tp in zip(model.parameters(), teacher.parameters()) if p.requires_grad]
+        for p, r in zip(params, refs):
+            assert p.shape == r.shape
+    elif origin == "zero" and has_lora_adapter(model):
+        raise ValueError("L1/L0 regularization is not supported for LORA!")
+    return loss + norms.weight_regulariser(params, refs, l1, l0).to(loss.dtype)
 
 
 class MMTrainerForgetting(_TrainerBase):

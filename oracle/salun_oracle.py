@@ -101,3 +101,40 @@ def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: np.ndarray, exp
     p = p - step_size * (m / denom)                             # addcdiv_(exp_avg, denom, -step_size)
     new_param = torch.from_numpy(p.astype(f)).to(torch.bfloat16).reshape(param.shape)
     return new_param, m.reshape(exp_avg.shape), v.reshape(exp_avg_sq.shape)
+
+
+def grad_sqnorm(grads, masks=None) -> float:
+    """sum over tensors of sum((g * mask)^2) in double — the square of torch.nn.utils.clip_grad_norm_'s total
+    norm (HF Trainer default max_grad_norm = 1.0; the override is commented out at mm/forget.py:151)."""
+    total = 0.0
+    for i, g in enumerate(grads):
+        x = g.detach().float().cpu().numpy().astype(np.float64).reshape(-1)
+        if masks is not None and masks[i] is not None:
+            x = np.where(np.asarray(masks[i]).reshape(-1) != 0, x, 0.0)
+        total += float(np.dot(x, x))
+    return total
+
+
+def clip_coef(sumsq: float, max_norm: float) -> np.float32:
+    """clip_coef_clamped of torch.nn.utils.clip_grad_norm_: min(1, max_norm / (total_norm + 1e-6))."""
+    return np.float32(min(1.0, max_norm / (np.sqrt(sumsq) + 1e-6)))
+
+
+def scale_grad(grad: torch.Tensor, coef) -> torch.Tensor:
+    """grad.mul_(coef) on a bf16 gradient: fp32 product, one rounding to bf16."""
+    g = grad.detach().float().cpu().numpy().astype(np.float32) * np.float32(coef)
+    return torch.from_numpy(g.astype(np.float32)).to(torch.bfloat16)
+
+
+def param_l1l0(params, refs=None) -> tuple[float, float]:
+    """(||cat(p - ref)||_1, ||cat(p - ref)||_0) of mm/trainer.py:451-481 / nlp/dataloader.py:461-483; `p - ref`
+    is a bf16 tensor in the reference (fp32 subtraction rounded to bf16); sums in double."""
+    l1 = l0 = 0.0
+    for i, p in enumerate(params):
+        d = p.detach().to(torch.bfloat16).cpu()
+        if refs is not None:
+            d = d - refs[i].detach().to(torch.bfloat16).cpu()
+        x = d.float().numpy().astype(np.float64).reshape(-1)
+        l1 += float(np.abs(x).sum())
+        l0 += float(np.count_nonzero(x))
+    return l1, l0

@@ -142,3 +142,29 @@ def test_adamw_oracle_close_to_torch():
     st = opt.state[p_ref]
     assert np.allclose(m, st["exp_avg"].numpy(), rtol=1e-5, atol=1e-9)
     assert np.allclose(v, st["exp_avg_sq"].numpy(), rtol=1e-5, atol=1e-12)
+
+
+def test_norm_oracles_match_the_torch_calls_the_reference_makes():
+    """clip_grad_norm_ (HF Trainer default max_grad_norm = 1.0) and torch.norm(torch.cat(params), p) (mm/trainer.py:478-481)."""
+    g = torch.Generator().manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(33, 7, generator=g)), torch.nn.Parameter(torch.randn(101, generator=g))]
+    for p in ps:
+        p.grad = (0.3 * torch.randn(p.shape, generator=g)).to(torch.bfloat16).float()
+    before = [p.grad.to(torch.bfloat16) for p in ps]
+    ss = SO.grad_sqnorm(before)
+    coef = SO.clip_coef(ss, 1.0)
+    total = torch.nn.utils.clip_grad_norm_(ps, 1.0)
+    assert abs(ss ** 0.5 - total.item()) <= 1e-6 * total.item()
+    assert float(coef) < 1.0
+    for p, b in zip(ps, before):
+        assert torch.allclose(SO.scale_grad(b, coef).float(), p.grad, atol=0, rtol=2 ** -8)
+    assert SO.clip_coef(1e-4, 1.0) == 1.0
+    a = [torch.randn(33, 7, generator=g).to(torch.bfloat16), torch.randn(9, generator=g).to(torch.bfloat16)]
+    b = [x.clone() for x in a]
+    b[0][3] += 0.5
+    cat = torch.cat([(x - y).view(-1) for x, y in zip(a, b)])
+    l1, l0 = SO.param_l1l0(a, b)
+    assert l1 == torch.norm(cat.float(), p=1).item() and l0 == torch.norm(cat.float(), p=0).item() == 7.0
+    l1z, l0z = SO.param_l1l0(a)
+    assert abs(l1z - torch.norm(torch.cat([x.view(-1) for x in a]).float(), p=1).item()) <= 1e-5 * l1z
+    assert l0z == sum(int((x != 0).sum()) for x in a)
