@@ -61,6 +61,36 @@ __device__ __forceinline__ float merge_lse(const float2* part, int n) {
   return m + logf(s);
 }
 
+// Student and teacher statistics in ONE round trip to L2: every lane fetches its (up to 4 + 4) partials before any
+// arithmetic.  n <= 128 tiles (vocabularies up to 32768) take the register path; larger ones fall back to the loops.
+__device__ __forceinline__ void merge_lse2(const float2* ps, const float2* pt, int n, float& lse_s, float& lse_t) {
+  if (n > 128) {
+    lse_s = merge_lse(ps, n);
+    lse_t = merge_lse(pt, n);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  float2 a[4], b[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = lane + 32 * k;
+    a[k] = (i < n) ? ps[i] : make_float2(-INFINITY, 0.f);
+    b[k] = (i < n) ? pt[i] : make_float2(-INFINITY, 0.f);
+  }
+  const float ma = warp_max(fmaxf(fmaxf(a[0].x, a[1].x), fmaxf(a[2].x, a[3].x)));
+  const float mb = warp_max(fmaxf(fmaxf(b[0].x, b[1].x), fmaxf(b[2].x, b[3].x)));
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (lane + 32 * k < n) {
+      sa += a[k].y * exp2f((a[k].x - ma) * kLog2e);
+      sb += b[k].y * exp2f((b[k].x - mb) * kLog2e);
+    }
+  }
+  lse_s = ma + logf(warp_sum(sa));
+  lse_t = mb + logf(warp_sum(sb));
+}
+
 template <int kThreads>
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -72,13 +102,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return warp_sum(t);  // every thread holds the total
 }
 
+// bf16 -> fp32 is a 16-bit shift: one SHF / LOP per element (the cuda_bf16 conversion emits PRMT + SHF)
 __device__ __forceinline__ void unpack8(const uint4& raw, float (&x)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 f = __bfloat1622float2(h[j]);
-    x[2 * j] = f.x;
-    x[2 * j + 1] = f.y;
+    x[2 * j] = __uint_as_float(w[j] << 16);
+    x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
@@ -147,8 +177,8 @@ __global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossPa
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
   const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
-  const float lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
-  const float lse_t = merge_lse(a.ref_lse_part + row * a.n_vtiles, a.n_vtiles);
+  float lse_s, lse_t;
+  merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, lse_s, lse_t);
   const float nls2 = -lse_s * kLog2e, nlt2 = -lse_t * kLog2e, dlse = lse_s - lse_t;
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
@@ -244,8 +274,9 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
   __nv_bfloat16* z = a.logits + row * a.ld;
   const __nv_bfloat16* zr = kNeedsRef ? a.ref_logits + row * a.ref_ld : nullptr;
   RowConsts c;
-  c.lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
-  const float lse_t = kNeedsRef ? merge_lse(a.ref_lse_part + row * a.n_vtiles, a.n_vtiles) : 0.f;
+  float lse_t = 0.f;
+  if constexpr (kNeedsRef) merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, c.lse_s, lse_t);
+  else c.lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
   c.nls2 = -c.lse_s * kLog2e;
   c.nlt2 = -lse_t * kLog2e;
   c.dlse = lse_t - c.lse_s;
@@ -304,6 +335,139 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
         float p, aux, st = 0.f, ls = 0.f;
         RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, c, p, aux, st, ls);
         x[j] = (c0 + j < a.vocab) ? RowTerm<kKind, kBetaOne>::grad(p, aux, g, gstat) : 0.f;
+      }
+    }
+    reinterpret_cast<uint4*>(z)[v] = pack8(x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NPO, beta = 1 (the shipped recipe: mm/trainer.py:343-353 with loss_beta = 1) — the headline row pass.
+// The generic two-pass kernel above spends 7 MUFU operations per logit and is bound by the XU pipe (83 % busy
+// in ncu) at a clock the tensor-heavy step has already pulled down.  This version needs 3.5:
+//   * one reciprocal serves four logits (1 / (B0 B1 B2 B3) unfolded with six multiplies; B = p + q + 1e-8 lies
+//     in [1e-8, 2], so the product of four stays a normal fp32 number);
+//   * one logarithm serves four logits (sum_j log(1 + t_j) = -log2 prod_j (1 - s_j); each factor >= 5e-9);
+//   * pass 1 parks s = t / (1 + t) in shared memory as fp32 (up to kNpoCacheVecs 8-logit vectors per row: two
+//     CTAs of 96 KB per SM), so pass 2 only re-forms p = exp(z - lse) and combines: dz = g (s - p S).
+// Vectors beyond the cache (vocabularies above 24576 keep 3/4 of the row cached) recompute s in pass 2.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kNpoCacheVecs = 3072;  // 3072 x 8 fp32 = 96 KB
+
+struct Npo8 {
+  float p[8], s[8];
+};
+
+// p, s of eight logits; adds sum(s) to stat and log2 prod(1 - s) to lossl2 (negative of the loss in log2 units)
+__device__ __forceinline__ void npo8_eval(const float (&x)[8], const float (&r)[8], float nls2, float nlt2, Npo8& o,
+                                          float& stat, float& lossl2, bool want_loss) {
+  float A[8], B[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o.p[j] = ptx::ex2_approx(fmaf(x[j], kLog2e, nls2));
+    A[j] = ptx::ex2_approx(fmaf(r[j], kLog2e, nlt2)) + 1e-8f;
+    B[j] = o.p[j] + A[j];
+  }
+#pragma unroll
+  for (int h = 0; h < 8; h += 4) {
+    const float b01 = B[h] * B[h + 1], b23 = B[h + 2] * B[h + 3];
+    const float inv = ptx::rcp_approx(b01 * b23);
+    const float i01 = inv * b23, i23 = inv * b01;  // 1 / b01, 1 / b23
+    const float i0 = i01 * B[h + 1], i1 = i01 * B[h], i2 = i23 * B[h + 3], i3 = i23 * B[h + 2];
+    o.s[h] = o.p[h] * i0;
+    o.s[h + 1] = o.p[h + 1] * i1;
+    o.s[h + 2] = o.p[h + 2] * i2;
+    o.s[h + 3] = o.p[h + 3] * i3;
+    stat += (o.s[h] + o.s[h + 1]) + (o.s[h + 2] + o.s[h + 3]);
+    if (want_loss) lossl2 += ptx::lg2_approx(((A[h] * i0) * (A[h + 1] * i1)) * ((A[h + 2] * i2) * (A[h + 3] * i3)));
+  }
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 2) rowloss_npo1_kernel(const RowLossParams a, const int cache_vecs) {
+  extern __shared__ float4 s_cache[];  // [2][cache_vecs]: low / high half of each 8-logit vector (conflict-free float4 rows)
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  __nv_bfloat16* z = a.logits + row * a.ld;
+  const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
+  const int nvec = (int)(a.ld >> 3);
+  const int nfull = a.vocab >> 3;
+  const int ref_nvec = (int)(a.ref_ld >> 3);
+  const int ncache = a.write_grad ? min(cache_vecs, nfull) : 0;
+  // register double-buffering: the next vector pair is in flight while this one is being evaluated (the first pair
+  // while the row statistics are merged)
+  uint4 nx = make_uint4(0, 0, 0, 0), nr = nx;
+  if ((int)threadIdx.x < nfull) {
+    nx = reinterpret_cast<const uint4*>(z)[threadIdx.x];
+    nr = reinterpret_cast<const uint4*>(zr)[threadIdx.x];
+  }
+  float lse_s, lse_t;
+  merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, lse_s, lse_t);
+  const float nls2 = -lse_s * kLog2e, nlt2 = -lse_t * kLog2e;
+  const float w = a.row_weight ? a.row_weight[row] : 1.f;
+  const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
+  float stat = 0.f, lossl2 = 0.f;
+  for (int v = threadIdx.x; v < nfull; v += kThreads) {
+    const uint4 cx = nx, cr = nr;
+    if (v + kThreads < nfull) {
+      nx = reinterpret_cast<const uint4*>(z)[v + kThreads];
+      nr = reinterpret_cast<const uint4*>(zr)[v + kThreads];
+    }
+    float x[8], r[8];
+    unpack8(cx, x);
+    unpack8(cr, r);
+    Npo8 o;
+    npo8_eval(x, r, nls2, nlt2, o, stat, lossl2, true);
+    if (v < ncache) {
+      s_cache[v] = make_float4(o.s[0], o.s[1], o.s[2], o.s[3]);
+      s_cache[cache_vecs + v] = make_float4(o.s[4], o.s[5], o.s[6], o.s[7]);
+    }
+  }
+  if (threadIdx.x == 0 && (a.vocab & 7)) {  // ragged tail: one partially valid vector, scalar arithmetic
+    RowConsts c;
+    c.nls2 = nls2; c.nlt2 = nlt2; c.dlse = lse_t - lse_s; c.lse_s = lse_s; c.beta = 1.f;
+    float x[8], r[8], l = 0.f;
+    unpack8(reinterpret_cast<const uint4*>(z)[nfull], x);
+    unpack8(nfull < ref_nvec ? reinterpret_cast<const uint4*>(zr)[nfull] : make_uint4(0, 0, 0, 0), r);
+    for (int j = 0; j < (a.vocab & 7); ++j) {
+      float p, aux;
+      RowTerm<CLEAR_KIND_NPO, true>::eval(x[j], r[j], c, p, aux, stat, l);
+    }
+    lossl2 -= l;
+  }
+  if (a.write_grad && (int)threadIdx.x < nvec) nx = reinterpret_cast<const uint4*>(z)[threadIdx.x];  // in flight across the barriers
+  stat = block_sum<kThreads>(stat, red);
+  lossl2 = block_sum<kThreads>(lossl2, red);
+  if (threadIdx.x == 0) a.loss_rows[row] = -lossl2 * kLn2 * w;
+  if (!a.write_grad) return;
+  const float gS = g * stat;
+  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+    float x[8];
+    unpack8(nx, x);
+    if (v + kThreads < nvec) nx = reinterpret_cast<const uint4*>(z)[v + kThreads];
+    if (v < ncache) {
+      const float4 lo = s_cache[v], hi = s_cache[cache_vecs + v];
+      const float s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaf(-ptx::ex2_approx(fmaf(x[j], kLog2e, nls2)), gS, g * s[j]);
+    } else if (v < nfull) {
+      float r[8], st = 0.f, ls = 0.f;
+      unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+      Npo8 o;
+      npo8_eval(x, r, nls2, nlt2, o, st, ls, false);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaf(-o.p[j], gS, g * o.s[j]);
+    } else {  // ragged / padding vectors
+      RowConsts c;
+      c.nls2 = nls2; c.nlt2 = nlt2; c.dlse = lse_t - lse_s; c.lse_s = lse_s; c.beta = 1.f;
+      float r[8];
+      unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
+      const int c0 = v << 3;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p, aux, st = 0.f, ls = 0.f;
+        RowTerm<CLEAR_KIND_NPO, true>::eval(x[j], r[j], c, p, aux, st, ls);
+        x[j] = (c0 + j < a.vocab) ? RowTerm<CLEAR_KIND_NPO, true>::grad(p, aux, g, gS) : 0.f;
       }
     }
     reinterpret_cast<uint4*>(z)[v] = pack8(x);
@@ -470,8 +634,19 @@ int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
       rowloss_twopass_kernel<CLEAR_KIND_ENTROPY, true, 512><<<grid, 512, 0, stream>>>(p);
       break;
     case CLEAR_KIND_NPO:
-      if (a->beta == 1.0f) rowloss_twopass_kernel<CLEAR_KIND_NPO, true, 512><<<grid, 512, 0, stream>>>(p);
-      else                 rowloss_twopass_kernel<CLEAR_KIND_NPO, false, 512><<<grid, 512, 0, stream>>>(p);
+      if (a->beta == 1.0f) {
+        static bool configured = false;
+        constexpr int kSmem = kNpoCacheVecs * 32;
+        if (!configured) {
+          CLEAR_CUDA_OK(cudaFuncSetAttribute(rowloss_npo1_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+          configured = true;
+        }
+        const int nfull = a->vocab >> 3;
+        const int cache_vecs = a->write_grad ? (nfull < kNpoCacheVecs ? nfull : kNpoCacheVecs) : 0;
+        rowloss_npo1_kernel<512><<<grid, 512, (size_t)cache_vecs * 32, stream>>>(p, cache_vecs);
+      } else {
+        rowloss_twopass_kernel<CLEAR_KIND_NPO, false, 512><<<grid, 512, 0, stream>>>(p);
+      }
       break;
     default:
       return fail(CLEAR_ERR_KIND, "clear_head_rowloss: unknown kind %d", a->kind);
