@@ -119,6 +119,19 @@ __device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
   return raw;
 }
 
+// two sums behind one pair of barriers
+template <int kThreads>
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = make_float2(a, b);
+  __syncthreads();
+  const float2 t = (lane < kThreads / 32) ? red[lane] : make_float2(0.f, 0.f);
+  return make_float2(warp_sum(t.x), warp_sum(t.y));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // CE: loss_row = lse - z[y]; dz = g (p - e_y).  Streaming, one pass.  (A2, A6c)
 // ---------------------------------------------------------------------------------------------------
@@ -383,10 +396,10 @@ __device__ __forceinline__ void npo8_eval(const float (&x)[8], const float (&r)[
   }
 }
 
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 2) rowloss_npo1_kernel(const RowLossParams a, const int cache_vecs) {
+template <int kThreads, int kMinBlocks, int kPf2 = 1>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(const RowLossParams a, const int cache_vecs) {
   extern __shared__ float4 s_cache[];  // [2][cache_vecs]: low / high half of each 8-logit vector (conflict-free float4 rows)
-  __shared__ float red[32];
+  __shared__ float2 red[32];
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
   const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
@@ -435,16 +448,26 @@ __global__ void __launch_bounds__(kThreads, 2) rowloss_npo1_kernel(const RowLoss
     }
     lossl2 -= l;
   }
-  if (a.write_grad && (int)threadIdx.x < nvec) nx = reinterpret_cast<const uint4*>(z)[threadIdx.x];  // in flight across the barriers
-  stat = block_sum<kThreads>(stat, red);
-  lossl2 = block_sum<kThreads>(lossl2, red);
+  // pass 2 is light (one MUFU per logit) and reads from L2: three vectors per thread are kept in flight, the first
+  // three across the barriers
+  uint4 px[kPf2];
+#pragma unroll
+  for (int k = 0; k < kPf2; ++k) {
+    px[k] = make_uint4(0, 0, 0, 0);
+    if (a.write_grad && (int)threadIdx.x + k * kThreads < nvec) px[k] = reinterpret_cast<const uint4*>(z)[threadIdx.x + k * kThreads];
+  }
+  const float2 tot = block_sum2<kThreads>(stat, lossl2, red);
+  stat = tot.x;
+  lossl2 = tot.y;
   if (threadIdx.x == 0) a.loss_rows[row] = -lossl2 * kLn2 * w;
   if (!a.write_grad) return;
   const float gS = g * stat;
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8];
-    unpack8(nx, x);
-    if (v + kThreads < nvec) nx = reinterpret_cast<const uint4*>(z)[v + kThreads];
+    unpack8(px[0], x);
+#pragma unroll
+    for (int k = 0; k + 1 < kPf2; ++k) px[k] = px[k + 1];
+    if (v + kPf2 * kThreads < nvec) px[kPf2 - 1] = reinterpret_cast<const uint4*>(z)[v + kPf2 * kThreads];
     if (v < ncache) {
       const float4 lo = s_cache[v], hi = s_cache[cache_vecs + v];
       const float s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -635,15 +658,18 @@ int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
       break;
     case CLEAR_KIND_NPO:
       if (a->beta == 1.0f) {
+        // 512 threads x 2 CTAs per SM with 96 KB of s-cache each measured best on B200 (tools/gpu_rowloss_ab.py, interleaved
+        // A/B per 4096 rows: 203 us; 1024 x 1 with the whole row cached 241 us; 256 x 4 / 48 KB 211 us; 384 x 3 / 64 KB 208 us;
+        // deeper register prefetch in either pass 207-217 us)
         static bool configured = false;
         constexpr int kSmem = kNpoCacheVecs * 32;
         if (!configured) {
-          CLEAR_CUDA_OK(cudaFuncSetAttribute(rowloss_npo1_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+          CLEAR_CUDA_OK(cudaFuncSetAttribute(rowloss_npo1_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
           configured = true;
         }
         const int nfull = a->vocab >> 3;
         const int cache_vecs = a->write_grad ? (nfull < kNpoCacheVecs ? nfull : kNpoCacheVecs) : 0;
-        rowloss_npo1_kernel<512><<<grid, 512, (size_t)cache_vecs * 32, stream>>>(p, cache_vecs);
+        rowloss_npo1_kernel<512, 2><<<grid, 512, (size_t)cache_vecs * 32, stream>>>(p, cache_vecs);
       } else {
         rowloss_twopass_kernel<CLEAR_KIND_NPO, false, 512><<<grid, 512, 0, stream>>>(p);
       }

@@ -20,6 +20,21 @@ part = torch.empty(N, nt, 2, device=dev); rpart = torch.empty_like(part)
 head.project(hid, w, z0, part); head.project(rh, w, zr, rpart)
 rows = torch.empty(N, device=dev)
 z = z0.clone()
+import os
+if os.environ.get("NPO_VARIANTS"):
+    res = {}
+    for rep in range(6):
+        for var in os.environ["NPO_VARIANTS"].split(","):
+            os.environ["CLEAR_NPO_VARIANT"] = var
+            z.copy_(z0); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            head.rowloss(KIND_NPO, z, part, rows, V, ref_logits=zr, ref_lse_part=rpart, grad_scale=1e-4)
+            b.record(); torch.cuda.synchronize()
+            res.setdefault(var, []).append(a.elapsed_time(b) * 1e3)
+    for var, ts in res.items():
+        print("variant", var, " ".join(f"{t:.1f}" for t in ts), "us  min", f"{min(ts):.1f}", flush=True)
+    sys.exit(0)
 out = {}
 for kind, name in ((KIND_CE, "ce"), (KIND_KL_FWD, "kl_fwd"), (KIND_KL_REV, "kl_rev"), (KIND_NPO, "npo"), (KIND_ENTROPY, "entropy")):
     ref = kind in (KIND_KL_FWD, KIND_KL_REV, KIND_NPO)
