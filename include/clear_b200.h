@@ -204,8 +204,18 @@ int64_t clear_saliency_chunk_elems(void);
 int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
                         int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
                         uint64_t* tie_scratch, int8_t* mask, void* stream);
+/* Same selection, bit-packed output: bit (i & 7) of byte i >> 3 is the mask of flat element i (layout offsets are
+ * multiples of 8, so tensors start on byte boundaries).  1/8 of the int8 format's traffic: 2.125 instead of 3 bytes
+ * per parameter and threshold here, 22.125 instead of 23 in the masked update. */
+int clear_saliency_mask_bits(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
+                             int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
+                             uint64_t* tie_scratch, uint8_t* mask_bits, void* stream);
+/* Converters between the reference's on-disk mask format (`with_{th}.pt`: int8, one byte per parameter,
+ * generate_mask.py:72-89) and the bit-packed one.  n elements; mask_bits holds (n + 7) / 8 bytes. */
+int clear_mask_pack(const int8_t* mask, int64_t n, uint8_t* mask_bits, void* stream);
+int clear_mask_unpack(const uint8_t* mask_bits, int64_t n, int8_t* mask, void* stream);
 /* Masked AdamW: g' = g * mask; torch _single_tensor_adam op order, fp32 states.
- * param, grad bf16; exp_avg, exp_avg_sq fp32; mask int8 (NULL = all ones). step >= 1. */
+ * param, grad bf16; exp_avg, exp_avg_sq fp32; mask int8 or mask_bits bit-packed (both NULL = all ones). step >= 1. */
 typedef struct ClearAdamWArgs {
   void* param;
   const void* grad;
@@ -217,6 +227,7 @@ typedef struct ClearAdamWArgs {
   int32_t step;
   const float* grad_scale_dev; /* optional device scalar (gradient-clipping coefficient): g = bf16(g * scale) first,
                                   like torch's in-place `grad.mul_(clip_coef)` on a bf16 gradient */
+  const uint8_t* mask_bits;    /* optional bit-packed mask (clear_saliency_mask_bits / clear_mask_pack); excludes `mask` */
 } ClearAdamWArgs;
 int clear_masked_adamw(const ClearAdamWArgs* args, void* stream);
 
@@ -224,15 +235,15 @@ int clear_masked_adamw(const ClearAdamWArgs* args, void* stream);
  * Whole-model reductions around the update (one pass over HBM each, bitwise reproducible).
  * partials: double workspace of clear_reduce_partials_elems() elements; out: device doubles;
  * accumulate != 0 adds to *out (tensor-by-tensor use), else overwrites.
- *   clear_grad_sqnorm: out[0] (+)= sum (grad * mask)^2       — torch.nn.utils.clip_grad_norm_ (HF Trainer's
+ *   clear_grad_sqnorm: out[0] (+)= sum (grad * mask)^2 (mask int8 or bit-packed or none) — clip_grad_norm_ (HF Trainer's
  *                      default max_grad_norm = 1.0; the override is commented out at mm/forget.py:151)
  *   clear_clip_coef:   coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))
  *   clear_param_l1l0:  out[0] (+)= sum |p - ref|, out[1] (+)= #{p != ref}; ref NULL = zeros
  *                      — torch.norm(torch.cat(params), p=1 / p=0), mm/trainer.py:451-481 (A9)
  * ------------------------------------------------------------------------------------------- */
 int64_t clear_reduce_partials_elems(void);
-int clear_grad_sqnorm(const void* grad, const int8_t* mask, int64_t n, double* partials, double* out, int accumulate,
-                      void* stream);
+int clear_grad_sqnorm(const void* grad, const int8_t* mask, const uint8_t* mask_bits, int64_t n, double* partials,
+                      double* out, int accumulate, void* stream);
 int clear_clip_coef(const double* sumsq, double max_norm, float* coef, void* stream);
 /* grad[i] = bf16(grad[i] * *coef) in place (torch: grads.mul_(clip_coef_clamped)); the fused alternative is
  * ClearAdamWArgs.grad_scale_dev */

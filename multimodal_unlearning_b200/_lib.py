@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "clear_head_reduce_sequences", "clear_head_backward", "clear_saliency_accumulate",
     "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_chunk_elems", "clear_saliency_mask",
     "clear_masked_adamw", "clear_reduce_partials_elems", "clear_grad_sqnorm", "clear_clip_coef", "clear_param_l1l0",
-    "clear_param_l1_grad", "clear_grad_scale",
+    "clear_param_l1_grad", "clear_grad_scale", "clear_saliency_mask_bits", "clear_mask_pack", "clear_mask_unpack",
 )
 
 
@@ -61,7 +61,8 @@ class AdamWArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("mask", C.c_void_p), ("n", C.c_int64),
                 ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
-                ("weight_decay", C.c_double), ("step", C.c_int32), ("grad_scale_dev", C.c_void_p)]
+                ("weight_decay", C.c_double), ("step", C.c_int32), ("grad_scale_dev", C.c_void_p),
+                ("mask_bits", C.c_void_p)]
 
 
 _lib = None
@@ -100,7 +101,10 @@ def load() -> C.CDLL:
     lib.clear_masked_adamw.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]
     lib.clear_reduce_partials_elems.argtypes = []
     lib.clear_reduce_partials_elems.restype = C.c_int64
-    lib.clear_grad_sqnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.clear_grad_sqnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.clear_saliency_mask_bits.argtypes = lib.clear_saliency_mask.argtypes
+    lib.clear_mask_pack.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.clear_mask_unpack.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.clear_clip_coef.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     lib.clear_param_l1l0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.clear_param_l1_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]

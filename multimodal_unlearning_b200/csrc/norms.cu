@@ -39,30 +39,64 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
   return warp_sum_d(t);
 }
 
-// partials[blockIdx.x] = sum over this block's vectors of (g * mask)^2
-__global__ void __launch_bounds__(kRedThreads) sqnorm_kernel(const __nv_bfloat16* g, const int8_t* mask, int64_t n,
-                                                             double* partials) {
+// partials[blockIdx.x] = sum over this block's vectors of (g * mask)^2.  Four vectors (and their mask words) per thread
+// are in flight before any arithmetic.
+constexpr int kSqUnroll = 4;
+
+__device__ __forceinline__ uint32_t half_mask2(uint32_t two_bits) {  // bit 0 -> low half, bit 1 -> high half
+  return ((two_bits & 1u) ? 0x0000FFFFu : 0u) | ((two_bits & 2u) ? 0xFFFF0000u : 0u);
+}
+
+__global__ void __launch_bounds__(kRedThreads) sqnorm_kernel(const __nv_bfloat16* g, const int8_t* mask,
+                                                             const uint8_t* mask_bits, int64_t n, double* partials) {
   __shared__ double red[32];
   const int64_t nvec = n >> 3;
   const int64_t stride = (int64_t)gridDim.x * kRedThreads;
   double acc = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < nvec; i += stride) {
-    const uint4 raw = ld_stream16(reinterpret_cast<const uint4*>(g) + i);
-    uint2 mk = make_uint2(0x01010101u, 0x01010101u);
-    if (mask) mk = *reinterpret_cast<const uint2*>(mask + (i << 3));
-    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
-    float s = 0.f;
+  for (int64_t i0 = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i0 < nvec; i0 += stride * kSqUnroll) {
+    uint4 raw[kSqUnroll];
+    uint2 mk[kSqUnroll];
+    uint32_t mb[kSqUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t mb = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xFFu;
-      const float x = mb ? __bfloat162float(h[j]) : 0.f;
-      s = fmaf(x, x, s);
+    for (int u = 0; u < kSqUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      mk[u] = make_uint2(0x01010101u, 0x01010101u);
+      mb[u] = 0xFFu;
+      if (i < nvec) {
+        raw[u] = ld_stream16(reinterpret_cast<const uint4*>(g) + i);
+        if (mask) mk[u] = *reinterpret_cast<const uint2*>(mask + (i << 3));
+        if (mask_bits) mb[u] = mask_bits[i];
+      }
     }
-    acc += (double)s;
+#pragma unroll
+    for (int u = 0; u < kSqUnroll; ++u) {
+      uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+      if (mask) {  // int8 mask: any non-zero byte selects
+        const uint32_t lo = __vcmpne4(mk[u].x, 0u), hi = __vcmpne4(mk[u].y, 0u);  // 0xFF per selected element
+        w[0] &= __byte_perm(lo, 0, 0x1100);
+        w[1] &= __byte_perm(lo, 0, 0x3322);
+        w[2] &= __byte_perm(hi, 0, 0x1100);
+        w[3] &= __byte_perm(hi, 0, 0x3322);
+      } else if (mask_bits) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] &= half_mask2(mb[u] >> (2 * q));
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = __uint_as_float(w[q] << 16), b = __uint_as_float(w[q] & 0xffff0000u);
+        s = fmaf(a, a, s);
+        s = fmaf(b, b, s);
+      }
+      acc += (double)s;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int64_t i = nvec << 3; i < n; ++i) {
-      const float x = (!mask || mask[i]) ? __bfloat162float(g[i]) : 0.f;
+      bool on = !mask || mask[i];
+      if (mask_bits) on = (mask_bits[i >> 3] >> (i & 7)) & 1u;
+      const float x = on ? __bfloat162float(g[i]) : 0.f;
       acc += (double)(x * x);
     }
   }
@@ -192,15 +226,16 @@ extern "C" {
 
 int64_t clear_reduce_partials_elems(void) { return (int64_t)(device_sm_count() > 0 ? device_sm_count() : 148) * 8 * 2; }
 
-int clear_grad_sqnorm(const void* grad, const int8_t* mask, int64_t n, double* partials, double* out, int accumulate,
-                      void* stream_) {
+int clear_grad_sqnorm(const void* grad, const int8_t* mask, const uint8_t* mask_bits, int64_t n, double* partials,
+                      double* out, int accumulate, void* stream_) {
   if (!grad || !partials || !out) return fail(CLEAR_ERR_NULL, "clear_grad_sqnorm: null pointer");
   if (n <= 0) return fail(CLEAR_ERR_SHAPE, "clear_grad_sqnorm: n <= 0");
   if (reinterpret_cast<uintptr_t>(grad) & 15) return fail(CLEAR_ERR_ALIGN, "clear_grad_sqnorm: grad must be 16-byte aligned");
   if (mask && (reinterpret_cast<uintptr_t>(mask) & 7)) return fail(CLEAR_ERR_ALIGN, "clear_grad_sqnorm: mask must be 8-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int blocks = red_blocks(n);
-  sqnorm_kernel<<<blocks, kRedThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(grad), mask, n, partials);
+  if (mask && mask_bits) return fail(CLEAR_ERR_KIND, "clear_grad_sqnorm: pass mask or mask_bits, not both");
+  sqnorm_kernel<<<blocks, kRedThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(grad), mask, mask_bits, n, partials);
   finish_kernel<<<1, 32, 0, stream>>>(partials, blocks, 1, out, accumulate);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;

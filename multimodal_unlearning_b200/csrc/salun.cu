@@ -266,10 +266,26 @@ __device__ __forceinline__ bool speculate_take(int64_t rel, int64_t n, int64_t b
   return (unsigned long long)rel * (unsigned long long)total < (unsigned long long)budget * (unsigned long long)n;
 }
 
+// Eight mask elements of one thread (sel01[q]: bit 0 = element 2q, bit 16 = element 2q + 1), at flat element e
+// (a multiple of 8).  int8 format: one byte per parameter, the reference's `with_{th}.pt` dtype
+// (generate_mask.py:72).  Bit-packed format: bit (e & 7) of byte e >> 3, 1/8 of the traffic for the masked update.
+template <bool kPacked>
+__device__ __forceinline__ void store_mask8(void* mask, int64_t e, const uint32_t (&sel01)[4]) {
+  if constexpr (kPacked) {
+    // bits {0, 16} of four words -> bits {0, 2, 4, 6} and {16, 18, 20, 22} of one, then fold the upper half down by 15
+    const uint32_t x = sel01[0] + (sel01[1] << 2) + (sel01[2] << 4) + (sel01[3] << 6);
+    static_cast<uint8_t*>(mask)[e >> 3] = (uint8_t)((x | (x >> 15)) & 0xFFu);
+  } else {
+    *reinterpret_cast<uint2*>(static_cast<int8_t*>(mask) + e) =
+        make_uint2(__byte_perm(sel01[0], sel01[1], 0x6420), __byte_perm(sel01[2], sel01[3], 0x6420));
+  }
+}
+
 // Exact rewrite of one chunk given the number of ties before it.  Called by a whole CTA.
+template <bool kPacked>
 __device__ __noinline__ void mask_ranked_chunk(const __nv_bfloat16* acc, int64_t begin, int64_t end, uint32_t lo2,
                                                uint32_t hi2, unsigned long long prefix, unsigned long long budget,
-                                               uint32_t* wcnt /* [kChunkIters][kChunkThreads / 32] */, int8_t* mask) {
+                                               uint32_t* wcnt /* [kChunkIters][kChunkThreads / 32] */, void* mask) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kChunkThreads / 32;
   uint32_t before[kChunkIters];
@@ -310,8 +326,7 @@ __device__ __noinline__ void mask_ranked_chunk(const __nv_bfloat16* acc, int64_t
         if (t & 0xFFFF0000u) { if (rank < budget) kp |= 0xFFFF0000u; ++rank; }
         sel01[q] = (g | kp) & 0x00010001u;
       }
-      *reinterpret_cast<uint2*>(mask + e) =
-          make_uint2(__byte_perm(sel01[0], sel01[1], 0x6420), __byte_perm(sel01[2], sel01[3], 0x6420));
+      store_mask8<kPacked>(mask, e, sel01);
     }
   }
   __syncthreads();  // wcnt may be reused by the caller's next chunk
@@ -335,9 +350,9 @@ __device__ __forceinline__ void cmp_word(uint32_t w, uint32_t lo2, uint32_t hi2,
 
 constexpr int kChunksPerCta = 4;
 
-template <bool kFloatCmp>
+template <bool kFloatCmp, bool kPacked>
 __device__ __forceinline__ uint32_t mask_chunk_fast(const __nv_bfloat16* acc, int64_t begin, int64_t end, uint32_t lo2,
-                                                    uint32_t hi2, uint32_t take_all, int8_t* mask) {
+                                                    uint32_t hi2, uint32_t take_all, void* mask) {
   uint4 raw[kChunkIters];
 #pragma unroll
   for (int it = 0; it < kChunkIters; ++it) {
@@ -359,17 +374,17 @@ __device__ __forceinline__ uint32_t mask_chunk_fast(const __nv_bfloat16* acc, in
         packed += t01;
         sel01[q] = (g & 0x00010001u) | (t01 & take_all);
       }
-      *reinterpret_cast<uint2*>(mask + e) =
-          make_uint2(__byte_perm(sel01[0], sel01[1], 0x6420), __byte_perm(sel01[2], sel01[3], 0x6420));
+      store_mask8<kPacked>(mask, e, sel01);
     }
   }
   return (packed & 0xFFFFu) + (packed >> 16);
 }
 
+template <bool kPacked>
 __global__ void __launch_bounds__(kChunkThreads) mask_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
                                                              const int64_t* chunk_prefix, int n_segs, int64_t n_chunks,
                                                              const int64_t* select, int n_th, int th_index,
-                                                             unsigned long long* scratch, int8_t* mask) {
+                                                             unsigned long long* scratch, void* mask) {
   __shared__ uint32_t wsum[kChunksPerCta][kChunkThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t c0 = (int64_t)blockIdx.x * kChunksPerCta;
@@ -393,8 +408,8 @@ __global__ void __launch_bounds__(kChunkThreads) mask_kernel(const __nv_bfloat16
     const uint32_t lo2 = plo | (plo << 16), hi2 = phi | (phi << 16);
     const uint32_t take_all = speculate_take(c - first_chunk, seg_last - first_chunk, sel[1], sel[4]) ? 0xFFFFFFFFu : 0u;
     const bool float_ok = plo <= 0x7F80u && phi <= 0x7F80u;  // block-uniform
-    const uint32_t mine = float_ok ? mask_chunk_fast<true>(acc, begin, end, lo2, hi2, take_all, mask)
-                                   : mask_chunk_fast<false>(acc, begin, end, lo2, hi2, take_all, mask);
+    const uint32_t mine = float_ok ? mask_chunk_fast<true, kPacked>(acc, begin, end, lo2, hi2, take_all, mask)
+                                   : mask_chunk_fast<false, kPacked>(acc, begin, end, lo2, hi2, take_all, mask);
     const uint32_t tot = __reduce_add_sync(0xffffffffu, mine);
     if (lane == 0) wsum[i][warp] = tot;
   }
@@ -437,10 +452,11 @@ __global__ void __launch_bounds__(1024) tie_scan_kernel(const int64_t* chunk_pre
 }
 
 // Thread t of CTA b audits chunk b * 256 + t; the CTA then rewrites the chunks that guessed wrong.
+template <bool kPacked>
 __global__ void __launch_bounds__(kChunkThreads) tie_fix_kernel(const __nv_bfloat16* acc, const int64_t* seg_off,
                                                                 const int64_t* chunk_prefix, int n_segs, int64_t n_chunks,
                                                                 const int64_t* select, int n_th, int th_index,
-                                                                const unsigned long long* scratch, int8_t* mask) {
+                                                                const unsigned long long* scratch, void* mask) {
   __shared__ uint32_t wcnt[kChunkIters * (kChunkThreads / 32)];
   __shared__ int n_wrong;
   __shared__ int wrong[kChunkThreads];
@@ -469,8 +485,8 @@ __global__ void __launch_bounds__(kChunkThreads) tie_fix_kernel(const __nv_bfloa
     locate_chunk(cw, seg_off, chunk_prefix, n_segs, seg, first_chunk, begin, end);
     const int64_t* sel = select + ((size_t)seg * n_th + th_index) * kSelFields;
     const uint32_t plo = (uint32_t)sel[2], phi = (uint32_t)sel[3];
-    mask_ranked_chunk(acc, begin, end, plo | (plo << 16), phi | (phi << 16), scratch[cw] & ((1ull << kCountShift) - 1),
-                      (unsigned long long)sel[1], wcnt, mask);
+    mask_ranked_chunk<kPacked>(acc, begin, end, plo | (plo << 16), phi | (phi << 16),
+                               scratch[cw] & ((1ull << kCountShift) - 1), (unsigned long long)sel[1], wcnt, mask);
   }
 }
 
@@ -503,6 +519,8 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
 
 constexpr int kAdamVecs = 1;  // 128-bit parameter vectors per thread and iteration (loads issued before any math)
 
+// kPackedMask: `mask` is the bit-packed format (bit i & 7 of byte i >> 3): 22.125 instead of 23 bytes per parameter
+template <bool kPackedMask>
 __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const __nv_bfloat16* grad, float* exp_avg,
                                                     float* exp_avg_sq, const int8_t* mask, int64_t n, AdamConsts c) {
   const int64_t nvec = n >> 3;
@@ -522,7 +540,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
         m1[u] = reinterpret_cast<const float4*>(exp_avg)[2 * i + 1];
         v0[u] = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i];
         v1[u] = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i + 1];
-        mk[u] = mask ? *reinterpret_cast<const uint2*>(mask + (i << 3)) : make_uint2(0x01010101u, 0x01010101u);
+        if constexpr (kPackedMask) mk[u] = make_uint2(reinterpret_cast<const uint8_t*>(mask)[i], 0u);
+        else mk[u] = mask ? *reinterpret_cast<const uint2*>(mask + (i << 3)) : make_uint2(0x01010101u, 0x01010101u);
       }
     }
 #pragma unroll
@@ -535,7 +554,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
       float vv[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t mb = ((j < 4 ? mk[u].x : mk[u].y) >> (8 * (j & 3))) & 0xFFu;
+        const uint32_t mb = kPackedMask ? ((mk[u].x >> j) & 1u) : (((j < 4 ? mk[u].x : mk[u].y) >> (8 * (j & 3))) & 0xFFu);
         float g = mb ? __bfloat162float(gh[j]) : 0.f;  // grad *= mask
         if (c.grad_scale) g = __bfloat162float(__float2bfloat16_rn(__fmul_rn(g, gscale)));  // grad.mul_(clip_coef) in bf16
         ph[j] = __float2bfloat16_rn(adam_one(__bfloat162float(ph[j]), g, mm[j], vv[j], c));
@@ -549,9 +568,43 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int64_t i = nvec << 3; i < n; ++i) {
-      float g = (!mask || mask[i]) ? __bfloat162float(grad[i]) : 0.f;
+      const bool on = kPackedMask ? ((reinterpret_cast<const uint8_t*>(mask)[i >> 3] >> (i & 7)) & 1u) : (!mask || mask[i]);
+      float g = on ? __bfloat162float(grad[i]) : 0.f;
       if (c.grad_scale) g = __bfloat162float(__float2bfloat16_rn(__fmul_rn(g, gscale)));
       param[i] = __float2bfloat16_rn(adam_one(__bfloat162float(param[i]), g, exp_avg[i], exp_avg_sq[i], c));
+    }
+  }
+}
+
+// int8 mask (one byte per parameter, the on-disk `with_{th}.pt` format) <-> bit-packed mask.  One thread per 8 elements.
+__global__ void __launch_bounds__(256) mask_pack_kernel(const int8_t* mask, int64_t n, uint8_t* bits) {
+  const int64_t nbytes = (n + 7) >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
+    uint32_t b = 0;
+    if ((i << 3) + 8 <= n) {
+      const uint2 m = *reinterpret_cast<const uint2*>(mask + (i << 3));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b |= ((((j < 4 ? m.x : m.y) >> (8 * (j & 3))) & 0xFFu) ? 1u : 0u) << j;
+    } else {
+      for (int j = 0; (i << 3) + j < n; ++j) b |= (mask[(i << 3) + j] ? 1u : 0u) << j;
+    }
+    bits[i] = (uint8_t)b;
+  }
+}
+
+__global__ void __launch_bounds__(256) mask_unpack_kernel(const uint8_t* bits, int64_t n, int8_t* mask) {
+  const int64_t nbytes = (n + 7) >> 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
+    const uint32_t b = bits[i];
+    if ((i << 3) + 8 <= n) {
+      uint2 m;
+      m.x = (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21);
+      m.y = ((b >> 4) & 1u) | (((b >> 4) & 2u) << 7) | (((b >> 4) & 4u) << 14) | (((b >> 4) & 8u) << 21);
+      *reinterpret_cast<uint2*>(mask + (i << 3)) = m;
+    } else {
+      for (int j = 0; (i << 3) + j < n; ++j) mask[(i << 3) + j] = (int8_t)((b >> j) & 1u);
     }
   }
 }
@@ -569,6 +622,29 @@ int stream_grid(int64_t nvec, int threads) {
 }  // namespace clear
 
 using namespace clear;
+
+template <bool kPacked>
+static int saliency_mask_impl(const char* who, const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
+                              int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
+                              uint64_t* tie_scratch, void* mask, void* stream_) {
+  if (!acc || !seg_offsets_dev || !chunk_prefix_dev || !select || !tie_scratch || !mask)
+    return fail(CLEAR_ERR_NULL, "%s: null pointer", who);
+  if (n_segs <= 0 || n_chunks <= 0 || n_chunks > INT32_MAX || th_index < 0 || th_index >= n_th)
+    return fail(CLEAR_ERR_SHAPE, "%s: bad sizes", who);
+  if ((reinterpret_cast<uintptr_t>(acc) & 15) || (!kPacked && (reinterpret_cast<uintptr_t>(mask) & 7)) ||
+      (reinterpret_cast<uintptr_t>(tie_scratch) & 7))
+    return fail(CLEAR_ERR_ALIGN, "%s: acc must be 16-byte, mask and tie_scratch 8-byte aligned", who);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(acc);
+  unsigned long long* scratch = reinterpret_cast<unsigned long long*>(tie_scratch);
+  mask_kernel<kPacked><<<(unsigned)((n_chunks + kChunksPerCta - 1) / kChunksPerCta), kChunkThreads, 0, stream>>>(
+      a, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th, th_index, scratch, mask);
+  tie_scan_kernel<<<(unsigned)n_segs, 1024, 0, stream>>>(chunk_prefix_dev, scratch);
+  tie_fix_kernel<kPacked><<<(unsigned)((n_chunks + kChunkThreads - 1) / kChunkThreads), kChunkThreads, 0, stream>>>(
+      a, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th, th_index, scratch, mask);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" {
 
@@ -619,21 +695,32 @@ int64_t clear_saliency_chunk_elems(void) { return kChunk; }
 
 int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
                         int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
-                        uint64_t* tie_scratch, int8_t* mask, void* stream_) {
-  if (!acc || !seg_offsets_dev || !chunk_prefix_dev || !select || !tie_scratch || !mask)
-    return fail(CLEAR_ERR_NULL, "clear_saliency_mask: null pointer");
-  if (n_segs <= 0 || n_chunks <= 0 || n_chunks > INT32_MAX || th_index < 0 || th_index >= n_th)
-    return fail(CLEAR_ERR_SHAPE, "clear_saliency_mask: bad sizes");
-  if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(mask) & 7) || (reinterpret_cast<uintptr_t>(tie_scratch) & 7))
-    return fail(CLEAR_ERR_ALIGN, "clear_saliency_mask: acc must be 16-byte, mask and tie_scratch 8-byte aligned");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(acc);
-  unsigned long long* scratch = reinterpret_cast<unsigned long long*>(tie_scratch);
-  mask_kernel<<<(unsigned)((n_chunks + kChunksPerCta - 1) / kChunksPerCta), kChunkThreads, 0, stream>>>(
-      a, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th, th_index, scratch, mask);
-  tie_scan_kernel<<<(unsigned)n_segs, 1024, 0, stream>>>(chunk_prefix_dev, scratch);
-  tie_fix_kernel<<<(unsigned)((n_chunks + kChunkThreads - 1) / kChunkThreads), kChunkThreads, 0, stream>>>(
-      a, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th, th_index, scratch, mask);
+                        uint64_t* tie_scratch, int8_t* mask, void* stream) {
+  return saliency_mask_impl<false>("clear_saliency_mask", acc, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select, n_th,
+                                   th_index, tie_scratch, mask, stream);
+}
+
+int clear_saliency_mask_bits(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
+                             int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,
+                             uint64_t* tie_scratch, uint8_t* mask_bits, void* stream) {
+  return saliency_mask_impl<true>("clear_saliency_mask_bits", acc, seg_offsets_dev, chunk_prefix_dev, n_segs, n_chunks, select,
+                                  n_th, th_index, tie_scratch, mask_bits, stream);
+}
+
+int clear_mask_pack(const int8_t* mask, int64_t n, uint8_t* mask_bits, void* stream) {
+  if (!mask || !mask_bits) return fail(CLEAR_ERR_NULL, "clear_mask_pack: null pointer");
+  if (n <= 0) return fail(CLEAR_ERR_SHAPE, "clear_mask_pack: n <= 0");
+  if (reinterpret_cast<uintptr_t>(mask) & 7) return fail(CLEAR_ERR_ALIGN, "clear_mask_pack: mask must be 8-byte aligned");
+  mask_pack_kernel<<<stream_grid((n + 7) >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, n, mask_bits);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_mask_unpack(const uint8_t* mask_bits, int64_t n, int8_t* mask, void* stream) {
+  if (!mask || !mask_bits) return fail(CLEAR_ERR_NULL, "clear_mask_unpack: null pointer");
+  if (n <= 0) return fail(CLEAR_ERR_SHAPE, "clear_mask_unpack: n <= 0");
+  if (reinterpret_cast<uintptr_t>(mask) & 7) return fail(CLEAR_ERR_ALIGN, "clear_mask_unpack: mask must be 8-byte aligned");
+  mask_unpack_kernel<<<stream_grid((n + 7) >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask_bits, n, mask);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -646,6 +733,7 @@ int clear_masked_adamw(const ClearAdamWArgs* a, void* stream) {
        reinterpret_cast<uintptr_t>(a->exp_avg_sq)) & 15)
     return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: tensors must be 16-byte aligned");
   if (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)) return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: mask must be 8-byte aligned");
+  if (a->mask && a->mask_bits) return fail(CLEAR_ERR_KIND, "clear_masked_adamw: pass mask or mask_bits, not both");
   // Scalar prologue of torch.optim.adam._single_tensor_adam, in double like the Python floats there.
   AdamConsts c;
   c.decay = (float)(1.0 - a->lr * a->weight_decay);
@@ -658,9 +746,14 @@ int clear_masked_adamw(const ClearAdamWArgs* a, void* stream) {
   c.bc2_sqrt = (float)sqrt(bc2);
   c.eps = (float)a->eps;
   c.grad_scale = a->grad_scale_dev;
-  adamw_kernel<<<stream_grid(a->n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(a->param), static_cast<const __nv_bfloat16*>(a->grad), a->exp_avg, a->exp_avg_sq,
-      a->mask, a->n, c);
+  if (a->mask_bits)
+    adamw_kernel<true><<<stream_grid(a->n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__nv_bfloat16*>(a->param), static_cast<const __nv_bfloat16*>(a->grad), a->exp_avg, a->exp_avg_sq,
+        reinterpret_cast<const int8_t*>(a->mask_bits), a->n, c);
+  else
+    adamw_kernel<false><<<stream_grid(a->n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__nv_bfloat16*>(a->param), static_cast<const __nv_bfloat16*>(a->grad), a->exp_avg, a->exp_avg_sq,
+        a->mask, a->n, c);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }

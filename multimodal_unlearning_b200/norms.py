@@ -66,13 +66,21 @@ def grad_sqnorm(grads: Sequence[torch.Tensor], masks: Sequence[torch.Tensor | No
     for i, g in enumerate(grads):
         gf = _flat_bf16(g, "grad_sqnorm")
         m = masks[i] if masks is not None else None
+        m8 = mb = None
         if m is not None:
-            if m.dtype != torch.int8 or m.numel() != gf.numel() or not m.is_cuda:
-                raise RuntimeError("grad_sqnorm: mask must be a CUDA int8 tensor of the gradient's size")
+            if not m.is_cuda:
+                raise RuntimeError("grad_sqnorm: mask must be a CUDA tensor")
             m = m.contiguous()
-            if m.data_ptr() % 8:
-                m = m.clone()
-        _lib.check(lib.clear_grad_sqnorm(gf.data_ptr(), m.data_ptr() if m is not None else None, gf.numel(),
+            if m.dtype == torch.uint8:      # bit-packed (salun.pack_mask / SaliencyState.mask_flat(packed=True))
+                if m.numel() != (gf.numel() + 7) // 8:
+                    raise RuntimeError("grad_sqnorm: packed mask must hold ceil(numel / 8) bytes")
+                mb = m
+            elif m.dtype == torch.int8 and m.numel() == gf.numel():
+                m8 = m.clone() if m.data_ptr() % 8 else m
+            else:
+                raise RuntimeError("grad_sqnorm: mask must be int8 of the gradient's size or bit-packed uint8")
+        _lib.check(lib.clear_grad_sqnorm(gf.data_ptr(), m8.data_ptr() if m8 is not None else None,
+                                         mb.data_ptr() if mb is not None else None, gf.numel(),
                                          part.data_ptr(), out.data_ptr(), 1, _stream()), "clear_grad_sqnorm")
     return out
 

@@ -118,16 +118,20 @@ class SaliencyState:
         self.hist = hist
         return sel
 
-    def mask_flat(self, sel: torch.Tensor, th_index: int, out: torch.Tensor | None = None) -> torch.Tensor:
-        """int8 mask of one threshold, flat in this layout."""
+    def mask_flat(self, sel: torch.Tensor, th_index: int, out: torch.Tensor | None = None,
+                  packed: bool = False) -> torch.Tensor:
+        """Mask of one threshold, flat in this layout: int8 (one byte per parameter, the reference's format) or,
+        with packed=True, uint8 bit-packed (bit i & 7 of byte i >> 3; layout.total / 8 bytes)."""
         lib = _lib.load()
         lay = self.layout
         if out is None:
-            out = torch.empty(lay.total, dtype=torch.int8, device=self.device)
+            out = (torch.empty(lay.total // 8, dtype=torch.uint8, device=self.device) if packed
+                   else torch.empty(lay.total, dtype=torch.int8, device=self.device))
         scratch = torch.empty(lay.n_chunks + 1, dtype=torch.int64, device=self.device)
-        _lib.check(lib.clear_saliency_mask(self.acc.data_ptr(), self.seg_off.data_ptr(), self.chunk_prefix.data_ptr(),
-                                           len(lay.names), lay.n_chunks, sel.data_ptr(), sel.shape[1], th_index,
-                                           scratch.data_ptr(), out.data_ptr(), _stream()), "clear_saliency_mask")
+        fn = lib.clear_saliency_mask_bits if packed else lib.clear_saliency_mask
+        _lib.check(fn(self.acc.data_ptr(), self.seg_off.data_ptr(), self.chunk_prefix.data_ptr(), len(lay.names),
+                      lay.n_chunks, sel.data_ptr(), sel.shape[1], th_index, scratch.data_ptr(), out.data_ptr(),
+                      _stream()), "clear_saliency_mask_bits" if packed else "clear_saliency_mask")
         self.launches += 3
         return out
 
@@ -137,6 +141,40 @@ class SaliencyState:
         for j, th in enumerate(thresholds):
             flat = self.mask_flat(sel, j)
             yield th, {n: self.layout.view(flat, i) for i, n in enumerate(self.layout.names)}
+
+
+def pack_mask(mask: torch.Tensor) -> torch.Tensor:
+    """int8 / bool mask (any shape, CUDA) -> bit-packed uint8 [ceil(numel / 8)] (bit i & 7 of byte i >> 3)."""
+    if not mask.is_cuda:
+        raise RuntimeError("pack_mask: CUDA tensors only")
+    m = mask.to(torch.int8).contiguous().view(-1)
+    if m.data_ptr() % 8:
+        m = m.clone()
+    bits = torch.empty((m.numel() + 7) // 8, dtype=torch.uint8, device=m.device)
+    _lib.check(_lib.load().clear_mask_pack(m.data_ptr(), m.numel(), bits.data_ptr(), _stream()), "clear_mask_pack")
+    return bits
+
+
+def unpack_mask(bits: torch.Tensor, shape: Sequence[int]) -> torch.Tensor:
+    """bit-packed uint8 -> int8 mask of `shape` (the reference's `with_{th}.pt` element format)."""
+    n = int(torch.Size(shape).numel())
+    if not bits.is_cuda or bits.dtype != torch.uint8 or bits.numel() != (n + 7) // 8:
+        raise RuntimeError("unpack_mask: need a CUDA uint8 tensor of ceil(numel / 8) bytes")
+    out = torch.empty(n, dtype=torch.int8, device=bits.device)
+    _lib.check(_lib.load().clear_mask_unpack(bits.contiguous().data_ptr(), n, out.data_ptr(), _stream()), "clear_mask_unpack")
+    return out.view(tuple(shape))
+
+
+def load_masks(path: str, device="cuda", packed: bool = True) -> dict:
+    """Read one of the reference's mask files (`with_{th}.pt` = torch.save(dict name -> int8 tensor of the parameter's
+    shape), generate_mask.py:72-89) onto the GPU; packed=True converts each tensor to the bit-packed format that
+    MaskedAdamW consumes (1 bit instead of 1 byte per parameter in HBM)."""
+    raw = torch.load(path, map_location="cpu")
+    out = {}
+    for name, m in raw.items():
+        m = m.to(device=device, dtype=torch.int8)
+        out[name] = pack_mask(m) if packed else m
+    return out
 
 
 def save_gradient_ratio(forget_loader: Iterable, model: torch.nn.Module, criterion, cfg) -> None:
@@ -172,11 +210,28 @@ class MaskedAdamW(torch.optim.Optimizer):
         self.max_grad_norm = max_grad_norm
         self.last_grad_norm = None  # device fp64 [1] after a clipped step
 
-    def set_mask(self, param: torch.Tensor, mask: torch.Tensor | None) -> None:
+    def set_mask(self, param: torch.Tensor, mask: torch.Tensor | None, packed: bool = True) -> None:
+        """mask: int8 / bool of the parameter's shape, or an already bit-packed uint8 [ceil(numel / 8)] tensor.
+        Stored bit-packed by default (0.875 GB instead of 7 GB for a 7 B-parameter model)."""
         if mask is None:
             self.masks.pop(param, None)
+            return
+        mask = mask.to(device=param.device)
+        if mask.dtype == torch.uint8 and mask.dim() == 1 and mask.numel() == (param.numel() + 7) // 8 and mask.numel() != param.numel():
+            self.masks[param] = mask.contiguous()
+        elif mask.numel() != param.numel():
+            raise RuntimeError("set_mask: mask must have the parameter's number of elements (or be its bit-packed form)")
+        elif packed:
+            self.masks[param] = pack_mask(mask)
         else:
-            self.masks[param] = mask.to(device=param.device, dtype=torch.int8).contiguous()
+            self.masks[param] = mask.to(torch.int8).contiguous()
+
+    def set_masks_from_file(self, path: str, model: torch.nn.Module) -> None:
+        """Attach the masks of one of the reference's `with_{th}.pt` files to this optimizer's parameters."""
+        named = dict(model.named_parameters())
+        for name, bits in load_masks(path, device=next(model.parameters()).device).items():
+            if name in named:
+                self.masks[named[name]] = bits
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -205,8 +260,12 @@ class MaskedAdamW(torch.optim.Optimizer):
                 st["step"] += 1
                 g = p.grad.to(torch.bfloat16).contiguous()
                 m = self.masks.get(p)
+                bits = m if (m is not None and m.dtype == torch.uint8) else None
+                if bits is not None:
+                    m = None
                 a = _lib.AdamWArgs(param=p.data_ptr(), grad=g.data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
                                    exp_avg_sq=st["exp_avg_sq"].data_ptr(), mask=m.data_ptr() if m is not None else None,
+                                   mask_bits=bits.data_ptr() if bits is not None else None,
                                    n=p.numel(), lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
                                    weight_decay=group["weight_decay"], step=st["step"],
                                    grad_scale_dev=scale.data_ptr() if scale is not None else None)
@@ -219,8 +278,12 @@ def masked_adamw_flat(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Te
                       weight_decay=0.01, grad_scale: torch.Tensor | None = None) -> None:
     """One launch over a flat parameter buffer (the layout of FlatLayout).  `grad_scale`: optional device fp32
     scalar (norms.clip_coef) applied to the masked gradient first, rounded to bf16 like `grad.mul_(coef)`."""
+    bits = mask if (mask is not None and mask.dtype == torch.uint8) else None  # uint8 = bit-packed, int8 = one byte each
+    if bits is not None:
+        mask = None
     a = _lib.AdamWArgs(param=param.data_ptr(), grad=grad.data_ptr(), exp_avg=exp_avg.data_ptr(),
                        exp_avg_sq=exp_avg_sq.data_ptr(), mask=mask.data_ptr() if mask is not None else None,
+                       mask_bits=bits.data_ptr() if bits is not None else None,
                        n=param.numel(), lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
                        step=step, grad_scale_dev=grad_scale.data_ptr() if grad_scale is not None else None)
     _lib.check(_lib.load().clear_masked_adamw(C.byref(a), _stream()), "clear_masked_adamw")

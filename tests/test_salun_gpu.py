@@ -185,3 +185,107 @@ def test_masked_adamw_optimizer_matches_torch_adamw_when_mask_is_ones():
         p2.data = p2.data.to(torch.bfloat16).float()  # our parameters are stored in bf16 after every step
     assert (p1.float() - p2).abs().max().item() <= 2 ** -7 * p2.abs().max().item()
     assert torch.allclose(o1.state[p1]["exp_avg"], o2.state[p2]["exp_avg"], rtol=1e-5, atol=1e-9)
+
+
+# ---- bit-packed masks -------------------------------------------------------------
+def test_packed_masks_equal_packed_int8_masks():
+    """clear_saliency_mask_bits == np.packbits(clear_saliency_mask), on the tie-heavy / special-value tensors too."""
+    from multimodal_unlearning_b200 import salun
+    g = torch.Generator().manual_seed(0)
+    named = {"a": ((torch.randn(1000003, generator=g) * 4).round() / 4), "b": torch.randn(8, generator=g),
+             "c": torch.randn(3, 5, generator=g), "d": torch.randn(2048, 1024, generator=g), "e": torch.randn(1, generator=g)}
+    named["d"][:, ::3] = 0.0
+    named = {n: v.to(torch.bfloat16) for n, v in named.items()}
+    layout = salun.FlatLayout([(n, v.shape) for n, v in named.items()])
+    state = salun.SaliencyState(layout, "cuda:0")
+    state.accumulate_flat(_flat(layout, named, torch.bfloat16).cuda())
+    ths = (0.0, 0.1, 0.5, 0.999, 1.0)
+    sel = state.select(ths)
+    for j, th in enumerate(ths):
+        m8 = state.mask_flat(sel, j).cpu().numpy()
+        bits = state.mask_flat(sel, j, packed=True)
+        assert bits.dtype == torch.uint8 and bits.numel() == layout.total // 8
+        assert np.array_equal(bits.cpu().numpy(), np.packbits(m8.astype(np.uint8), bitorder="little")), th
+        # and the per-tensor slices are byte aligned: tensor i starts at byte offsets[i] / 8
+        want = SO.masks(named, (th,))[th]
+        for i, n in enumerate(layout.names):
+            got = salun.unpack_mask(bits[layout.offsets[i] // 8: layout.offsets[i] // 8 + (layout.numels[i] + 7) // 8],
+                                    named[n].shape)
+            assert np.array_equal(got.cpu().numpy(), want[n]), (th, n)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 64, 100_003])
+def test_pack_unpack_round_trip(n):
+    from multimodal_unlearning_b200 import salun
+    g = torch.Generator().manual_seed(n)
+    m = (torch.rand(n, generator=g) < 0.4).to(torch.int8)
+    bits = salun.pack_mask(m.cuda())
+    assert np.array_equal(bits.cpu().numpy(), np.packbits(m.numpy().astype(np.uint8), bitorder="little"))
+    assert torch.equal(salun.unpack_mask(bits, (n,)).cpu(), m)
+
+
+def test_masked_adamw_packed_mask_bit_exact():
+    """The update driven by the bit-packed mask equals the int8-mask update and the oracle, bit for bit."""
+    from multimodal_unlearning_b200 import salun
+    dev = torch.device("cuda:0")
+    n = 1_000_003
+    g = torch.Generator().manual_seed(4)
+    p = torch.randn(n, generator=g).to(torch.bfloat16)
+    mask = (torch.rand(n, generator=g) < 0.5).to(torch.int8)
+    grad = (0.01 * torch.randn(n, generator=g)).to(torch.bfloat16)
+    want_p, want_m, want_v = SO.adamw_step(p, grad, np.zeros(n, np.float32), np.zeros(n, np.float32), mask.numpy(), 1, lr=1e-3)
+    pd, md, vd = p.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    salun.masked_adamw_flat(pd, grad.to(dev), md, vd, salun.pack_mask(mask.to(dev)), 1, lr=1e-3)
+    assert torch.equal(pd.cpu().view(torch.int16), want_p.view(torch.int16))
+    assert np.array_equal(md.cpu().numpy().view(np.int32), want_m.view(np.int32))
+    assert np.array_equal(vd.cpu().numpy().view(np.int32), want_v.view(np.int32))
+
+
+def test_mask_files_round_trip_into_the_optimizer(tmp_path):
+    """save_gradient_ratio writes the reference's `with_{th}.pt` (dict name -> int8 tensor, generate_mask.py:72-89);
+    load_masks / set_masks_from_file read it back bit-packed; the packed update equals the int8 one."""
+    import types
+    from multimodal_unlearning_b200 import norms, salun
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(50, 16)
+            self.out = torch.nn.Linear(16, 50, bias=False)
+
+        def forward(self, input_ids, attention_mask=None, labels=None):
+            z = self.out(self.emb(input_ids)).float()
+            return types.SimpleNamespace(loss=torch.nn.functional.cross_entropy(z[:, :-1].reshape(-1, 50), labels[:, 1:].reshape(-1)))
+
+    model = Tiny().to(dev).to(torch.bfloat16)
+    ids = torch.randint(0, 50, (2, 9))
+    salun.save_gradient_ratio([(ids, ids, torch.ones_like(ids))], model, None, types.SimpleNamespace(save_dir=str(tmp_path)))
+    raw = torch.load(tmp_path / "with_0.5.pt")
+    assert set(raw) == {n for n, _ in model.named_parameters()}
+    for n, p in model.named_parameters():
+        assert raw[n].dtype == torch.int8 and raw[n].shape == p.shape and int(raw[n].sum()) == int(0.5 * p.numel())
+    packed = salun.load_masks(str(tmp_path / "with_0.5.pt"), device=dev)
+    for n, p in model.named_parameters():
+        assert packed[n].dtype == torch.uint8
+        assert torch.equal(salun.unpack_mask(packed[n], p.shape).cpu(), raw[n])
+    # two optimizers: masks from the file (packed) vs the same masks as int8; clipping active in both
+    import copy
+    m2 = copy.deepcopy(model)
+    o1 = salun.MaskedAdamW(model.parameters(), lr=1e-2, max_grad_norm=0.05)
+    o1.set_masks_from_file(str(tmp_path / "with_0.5.pt"), model)
+    o2 = salun.MaskedAdamW(m2.parameters(), lr=1e-2, max_grad_norm=0.05)
+    for (n, p) in m2.named_parameters():
+        o2.set_mask(p, raw[n].to(dev), packed=False)
+    for _ in range(2):
+        for pa, pb in zip(model.parameters(), m2.parameters()):
+            gr = torch.randn(pa.shape, device=dev).to(torch.bfloat16)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        o1.step()
+        o2.step()
+        assert o1.last_grad_norm.item() == o2.last_grad_norm.item()
+    for (n, pa), pb in zip(model.named_parameters(), m2.parameters()):
+        assert torch.equal(pa, pb), n
+        frozen = raw[n].to(dev) == 0
+        assert frozen.any() and not torch.equal(pa, torch.zeros_like(pa))

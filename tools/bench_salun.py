@@ -54,12 +54,27 @@ def run(layers=32, reps=3, peak_gbs=6525.2, adam=True):
     ms = timed(lambda: st.mask_flat(sel, 4, out=mask))
     out["mask(one threshold)"] = {"ms": ms, "bytes_per_param": 3, "gbs": 3 * P / ms / 1e6, "frac": 3 * P / ms / 1e6 / peak_gbs,
                                   "ones": int(mask.sum(dtype=torch.int64).item())}
+    bits = torch.empty(P // 8, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: st.mask_flat(sel, 4, out=bits, packed=True))
+    b = 2.125
+    out["mask_bits(one threshold)"] = {"ms": ms, "bytes_per_param": b, "gbs": b * P / ms / 1e6, "frac": b * P / ms / 1e6 / peak_gbs}
+    from multimodal_unlearning_b200 import norms
+    ms = timed(lambda: norms.clip_coef(norms.grad_sqnorm([grads], [bits]), 1.0))
+    out["grad_sqnorm(masked, packed)+clip_coef"] = {"ms": ms, "bytes_per_param": b, "gbs": b * P / ms / 1e6,
+                                                     "frac": b * P / ms / 1e6 / peak_gbs}
     if adam:
         param = torch.zeros(P, dtype=torch.bfloat16, device=dev)
         m = torch.zeros(P, dtype=torch.float32, device=dev)
         v = torch.zeros(P, dtype=torch.float32, device=dev)
         ms = timed(lambda: salun.masked_adamw_flat(param, grads, m, v, mask, 1))
         out["masked_adamw"] = {"ms": ms, "bytes_per_param": 23, "gbs": 23 * P / ms / 1e6, "frac": 23 * P / ms / 1e6 / peak_gbs}
+        coef = norms.clip_coef(norms.grad_sqnorm([grads], [bits]), 1.0)
+        ms = timed(lambda: salun.masked_adamw_flat(param, grads, m, v, bits, 1, grad_scale=coef))
+        b = 22.125
+        out["masked_adamw(packed mask, fused clip)"] = {"ms": ms, "bytes_per_param": b, "gbs": b * P / ms / 1e6,
+                                                        "frac": b * P / ms / 1e6 / peak_gbs}
+        ms = timed(lambda: norms.param_l1l0([param], [grads]))
+        out["param_l1l0(vs reference params)"] = {"ms": ms, "bytes_per_param": 4, "gbs": 4 * P / ms / 1e6, "frac": 4 * P / ms / 1e6 / peak_gbs}
     return out
 
 
