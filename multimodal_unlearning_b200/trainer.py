@@ -27,6 +27,7 @@ import torch
 from torch import nn
 
 from . import head, norms
+from .teacher_cache import TeacherCache
 from .head import KIND_CE, KIND_ENTROPY, KIND_KL_FWD, KIND_KL_REV, KIND_NPO
 
 try:  # transformers.Trainer needs `accelerate` to be *constructed*, not to be subclassed
@@ -231,6 +232,18 @@ class _Recipes:
         return surrogate + (value - surrogate).detach()
 
 
+def _teacher_cache(self) -> TeacherCache | None:
+    """Extension: `teacher_cache_gb=<float>` ctor kwarg (or a `teacher_cache` attribute) enables
+    replay of the frozen teacher's hidden states; absent / 0 = the reference's behaviour (teacher forward every step)."""
+    cache = getattr(self, "teacher_cache", None)
+    if cache is None:
+        gb = getattr(self, "teacher_cache_gb", 0) or 0
+        if gb > 0:
+            cache = TeacherCache(int(gb * (1 << 30)))
+            self.teacher_cache = cache
+    return cache
+
+
 def _regulariser(self, model, teacher, loss):
     """L1 / L0 weight regulariser (mm/trainer.py:451-481; nlp/dataloader.py:461-483).  The norm of the
     concatenation is the sum of per-tensor norms, so the 7 B-element torch.cat is not formed."""
@@ -265,6 +278,7 @@ class MMTrainerForgetting(_TrainerBase):
         self.loss_args = kwargs.pop("loss_args", {})
         self.block_rows = kwargs.pop("block_rows", None)   # extension: rows staged per pass of the head
         self.dpo_true = kwargs.pop("dpo_true", False)      # extension: App. B #4
+        self.teacher_cache_gb = kwargs.pop("teacher_cache_gb", 0)  # extension: replay of the frozen teacher (teacher_cache.py)
         if self.l1_lambda and self.l1_lambda != 0 and self.l_norm_from not in ("zero", "init"):
             raise ValueError(f"Invalid l_norm_from {self.l_norm_from}, should be 'zero' or 'init'")
         super().__init__(*args, **kwargs)
@@ -310,10 +324,19 @@ class MMTrainerForgetting(_TrainerBase):
         def tfwd(split, crop=False):
             if teacher is None:
                 raise RuntimeError(f"loss '{self.loss_type}' needs teacher_model")
+            cache = _teacher_cache(self)
+            keys = None
+            if cache is not None:
+                keys = TeacherCache.sample_keys(splits[split], image_token, tag="crop" if crop else "")
+                h = cache.lookup(keys)
+                if h is not None:
+                    return h.to(device), _locate_head(teacher)[2].weight.to(device)
             with torch.no_grad():
                 h, w = trunk_hidden(teacher, MMTrainerForgetting.to_device(next(teacher.parameters()).device, splits[split]))
                 if crop:
                     h = rows(h, split)
+            if cache is not None:
+                cache.store(keys, h)
             return h.to(device), w.to(device)
 
         r = _Recipes(fwd, tfwd, self.loss_beta, getattr(self, "loss_args", None) or {},
@@ -374,6 +397,7 @@ class CustomTrainerForgetting(_TrainerBase):
         self.l0_lambda = kwargs.pop("l0_lambda")
         self.block_rows = kwargs.pop("block_rows", None)
         self.dpo_true = kwargs.pop("dpo_true", False)
+        self.teacher_cache_gb = kwargs.pop("teacher_cache_gb", 0)
         super().__init__(*args, **kwargs)
         if self.oracle_model is not None:
             self.oracle_model.eval()
@@ -405,8 +429,17 @@ class CustomTrainerForgetting(_TrainerBase):
                 raise RuntimeError(f"loss '{self.loss_type}' needs oracle_model")
             ids, _, att = splits[split]
             tdev = next(teacher.parameters()).device
+            cache = _teacher_cache(self)
+            keys = None
+            if cache is not None:
+                keys = TeacherCache.sample_keys({"input_ids": ids, "attention_mask": att}, None)
+                h = cache.lookup(keys)
+                if h is not None:
+                    return h.to(device), _locate_head(teacher)[2].weight.to(device)
             with torch.no_grad():
                 h, w = trunk_hidden(teacher, {"input_ids": ids.to(tdev), "attention_mask": att.to(tdev)})
+            if cache is not None:
+                cache.store(keys, h)
             return h.to(device), w.to(device)
 
         r = _Recipes(fwd, tfwd, self.loss_beta, {}, getattr(self, "block_rows", None), "KL")

@@ -163,3 +163,80 @@ def test_save_gradient_ratio_dropin(tmp_path):
         for n in acc:
             assert hard[n].dtype == torch.int8 and tuple(hard[n].shape) == tuple(acc[n].shape)
             assert np.array_equal(hard[n].numpy(), want[th][n]), (th, n)
+
+
+# ---- frozen-teacher replay ----------------------------------------------------------
+class _CountCalls:
+    def __init__(self, module):
+        self.n = 0
+        self.h = module.register_forward_hook(lambda *a: setattr(self, "n", self.n + 1))
+
+
+@pytest.mark.parametrize("kind,loss_type", [("mm", "npo"), ("mm", "grad_diff_forget_kl_retain_kl"), ("nlp", "KL")])
+def test_teacher_cache_replays_the_same_loss_without_teacher_forwards(kind, loss_type):
+    from multimodal_unlearning_b200 import trainer as T
+    student, teacher, dev = _models(kind)
+    if kind == "mm":
+        inputs = {"retain": RH.mm_split(2, 64, 11), "forget": RH.mm_split(2, 64, 12), "idk": RH.mm_split(2, 64, 13)}
+        mk = lambda gb: types.SimpleNamespace(loss_type=loss_type, teacher_model=teacher, loss_beta=0.7, l1_lambda=0.0,
+                                              l0_lambda=0.0, l_norm_from="zero", loss_args={}, teacher_cache_gb=gb)
+        call = lambda fake, inp: T.MMTrainerForgetting.compute_loss(fake, student, inp)
+    else:
+        inputs = [RH.nlp_triple(2, 64, 21), RH.nlp_triple(2, 64, 22), RH.nlp_triple(2, 64, 23)]
+        mk = lambda gb: types.SimpleNamespace(loss_type=loss_type, oracle_model=teacher, loss_beta=1.0, l1_lambda=0.0,
+                                              l0_lambda=0.0, teacher_cache_gb=gb)
+        call = lambda fake, inp: T.CustomTrainerForgetting.compute_loss(fake, student, inp)
+    counter = _CountCalls(teacher)
+    plain = call(mk(0), inputs)
+    n_plain = counter.n
+    assert n_plain >= 1
+    cached = mk(1.0)
+    first = call(cached, inputs)           # fills the cache (teacher still runs)
+    assert counter.n == 2 * n_plain
+    student.zero_grad(set_to_none=True)
+    second = call(cached, inputs)          # replay: the teacher is not called at all
+    assert counter.n == 2 * n_plain
+    assert first.item() == plain.item() and second.item() == plain.item()
+    second.backward()
+    st = cached.teacher_cache.stats()
+    assert st["hits"] == n_plain and st["entries"] == 2 * n_plain and st["bytes"] > 0
+    # a batch with one changed token is a miss for that sample -> the teacher runs again, result unchanged semantics
+    if kind == "mm":
+        other = {k: dict(v) for k, v in inputs.items()}
+        ids = other["forget"]["input_ids"].clone()
+        ids[0, -1] = (ids[0, -1] + 1) % 1000
+        other["forget"]["input_ids"] = ids
+    else:
+        other = [tuple(x.clone() for x in t) for t in inputs]
+        other[1][0][0, 5] = (other[1][0][0, 5] + 1) % 1000
+    before = counter.n
+    changed = call(cached, other)
+    assert counter.n > before
+    assert changed.item() == call(mk(0), other).item()
+    counter.h.remove()
+
+
+def test_teacher_cache_lru_eviction_and_keys():
+    from multimodal_unlearning_b200.teacher_cache import TeacherCache
+    dev = torch.device("cuda:0")
+    c = TeacherCache(max_bytes=3 * 4 * 8 * 2)          # room for three [4, 8] bf16 rows
+    mk = lambda i: {"input_ids": torch.full((1, 4), i), "attention_mask": torch.ones(1, 4, dtype=torch.long)}
+    keys = [TeacherCache.sample_keys(mk(i), None)[0] for i in range(4)]
+    assert len(set(keys)) == 4 and all(len(k) == 16 for k in keys)
+    rows = [torch.full((1, 4, 8), float(i), dtype=torch.bfloat16, device=dev) for i in range(4)]
+    for i in range(3):
+        c.store([keys[i]], rows[i])
+    assert c.lookup([keys[0]]) is not None              # touch 0: 1 becomes least recently used
+    c.store([keys[3]], rows[3])
+    assert c.lookup([keys[1]]) is None and c.lookup([keys[0], keys[3]]).shape == (2, 4, 8)
+    assert c.stats()["bytes"] == 3 * 4 * 8 * 2
+    # attention mask and image bytes are part of the key
+    a = mk(7)
+    b = {**a, "attention_mask": torch.tensor([[0, 1, 1, 1]])}
+    assert TeacherCache.sample_keys(a, None) != TeacherCache.sample_keys(b, None)
+    img = {"input_ids": torch.tensor([[5, 9, 9, 2], [5, 1, 1, 2]]), "attention_mask": torch.ones(2, 4, dtype=torch.long),
+           "pixel_values": torch.zeros(1, 3, 2, 2)}
+    k0 = TeacherCache.sample_keys(img, image_token_id=9)
+    img2 = {**img, "pixel_values": torch.ones(1, 3, 2, 2)}
+    k1 = TeacherCache.sample_keys(img2, image_token_id=9)
+    assert k0[0] != k1[0] and k0[1] == k1[1]            # only the sample that owns the image changes
