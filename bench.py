@@ -169,6 +169,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-allreduce", action="store_true", help="diagnostic: skip the dW all-reduce at N > 1 (not a valid bench line)")
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: dW mean over ranks fused into the contraction (reduce-scatter in the epilogue over NVLink + "
+                         "multicast all-gather), or an NCCL all-reduce on a side stream")
     ap.add_argument("--no-salun", action="store_true", help="skip the SalUn mask / masked-AdamW HBM-roofline section")
     ap.add_argument("--salun-layers", type=int, default=32, help="Llama-2-7B layer count of the synthetic parameter list")
     args = ap.parse_args()
@@ -209,15 +213,31 @@ def main():
     ref_weight = weight.clone()
     labels = torch.randint(0, V, (n,), generator=g, device=dev)  # unused by NPO; part of the batch a step receives
 
-    reducer = D.GradReducer(average=True)
+    fused = world > 1 and args.allreduce == "fused" and not args.no_allreduce
+    reducer = D.FusedGradReducer((V, H), dev, average=True) if fused else D.GradReducer(average=True)
     dws = [None, None]
 
     def step(i, hid, rhid):
+        if fused:
+            target = reducer.begin()
+            res = head.head_loss_fwd_bwd(hid, weight, KIND_NPO, ref_hidden=rhid, ref_weight=ref_weight, beta=BETA,
+                                         block_rows=block_rows, dweight_target=target)
+            handle, dw = reducer.finish(target)    # (event, averaged dW) — valid for two steps
+            dws[i & 1] = (res, handle, dw)
+            return res
         res = head.head_loss_fwd_bwd(hid, weight, KIND_NPO, ref_hidden=rhid, ref_weight=ref_weight, beta=BETA,
                                      block_rows=block_rows)
-        handle = reducer.launch(res.dweight)
+        handle = None if args.no_allreduce else reducer.launch(res.dweight)
         dws[i & 1] = (res, handle)
         return res
+
+    def wait_reduced(handle):
+        if handle is None:
+            return
+        if fused:
+            torch.cuda.current_stream().wait_event(handle)
+        else:
+            reducer.wait(handle)
 
     def barrier():
         if world > 1:
@@ -242,7 +262,7 @@ def main():
             res = step(i, hidden, ref_hidden)
         for r_h in dws:
             if r_h is not None:
-                reducer.wait(r_h[1])
+                wait_reduced(r_h[1])
         e1.record()
         barrier()
     summ = st.summary()
@@ -283,7 +303,7 @@ def main():
             loss_host.copy_(r.loss, non_blocking=True)
         for r_h in dws:
             if r_h is not None:
-                reducer.wait(r_h[1])
+                wait_reduced(r_h[1])
 
     e2e_loop(max(2, args.warmup))
     barrier()
@@ -334,7 +354,11 @@ def main():
             "config": {"workload": WORKLOAD, "loss_type": "npo", "rows_per_gpu": n, "hidden": H, "vocab": V,
                        "block_rows": block_rows or head.DEFAULT_BLOCK_ROWS, "loss": loss_value,
                        "l2": "inputs larger than L2 (W 263 MB + hidden 2 x 67 MB + staged logits 2 x 525 MB vs 126 MB L2); no explicit flush",
-                       "dw_allreduce": "NCCL all-reduce(avg) of bf16 dW per step, overlapped with the next step" if world > 1 else "none (1 GPU)"},
+                       "dw_allreduce": ("SKIPPED (--no-allreduce diagnostic run)" if args.no_allreduce else
+                                        ("fused: dW contraction epilogue TMA-reduce-adds tiles into the owner rank's buffer over NVLink "
+                                         "(reduce-scatter), multimem.st all-gather through the NVSwitch multicast mapping, per step"
+                                         if fused else "NCCL all-reduce(avg) of bf16 dW per step, overlapped with the next step"))
+                                       if world > 1 else "none (1 GPU)"},
             "e2e": {"value": tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,

@@ -167,8 +167,24 @@ typedef struct ClearBackwardArgs {
    * along the vocabulary (split-K, fp32 reduce-add, one conversion pass) when its output tiles alone would leave
    * the last wave of SM pairs mostly idle.  NULL: never split. */
   float* dhidden_ws;
+  /* Fused gradient reduce-scatter (data parallel): n_peers > 0 and dweight_peers[r] = rank r's bf16
+   * [vocab, dweight_ld] accumulation buffer mapped into this process (symmetric memory over NVLink / NVSwitch).  The dW
+   * contraction's epilogue then reduce-adds (bf16, like DDP's bf16 gradient all-reduce) every output tile into the buffer
+   * of the rank that owns its rows (clear_head_dweight_slab) instead of writing `dweight`, which may be NULL.  The owners'
+   * slabs must have been zeroed, and all ranks synchronised, before any rank launches; clear_dweight_allgather finishes
+   * the all-reduce. */
+  void* dweight_peers[8];
+  int32_t n_peers;
 } ClearBackwardArgs;
 int clear_head_backward(const ClearBackwardArgs* args, void* stream);
+/* Rows [row0, row1) of dW that `rank` owns among n_peers (contiguous slabs of whole output tiles). */
+int clear_head_dweight_slab(int32_t vocab, int32_t n_peers, int32_t rank, int32_t cta_group, int32_t* row0, int32_t* row1);
+/* All-gather half of the fused all-reduce: rows [row0, row1) of this rank's reduced slab, times `scale` (1 / world size
+ * for DDP's mean), are written to the same rows of EVERY rank's buffer — through the NVSwitch multicast mapping of the
+ * buffers when multicast_buf != NULL (one multimem.st per 16 bytes; the switch replicates), else by plain peer stores to
+ * each of the n_peers pointers.  bf16, row stride ld elements, hidden_dim a multiple of 8. */
+int clear_dweight_allgather(const void* local_buf, void* multicast_buf, void* const* peer_bufs, int32_t n_peers, int64_t ld,
+                            int32_t row0, int32_t row1, int32_t hidden_dim, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SalUn saliency mask (methods/salun/generate_mask.py:17-89) and the masked update.

@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = (
     "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_chunk_elems", "clear_saliency_mask",
     "clear_masked_adamw", "clear_reduce_partials_elems", "clear_grad_sqnorm", "clear_clip_coef", "clear_param_l1l0",
     "clear_param_l1_grad", "clear_grad_scale", "clear_saliency_mask_bits", "clear_mask_pack", "clear_mask_unpack",
+    "clear_head_dweight_slab", "clear_dweight_allgather",
 )
 
 
@@ -54,7 +55,8 @@ class BackwardArgs(C.Structure):
                 ("dlogits_ld", C.c_int64), ("hidden_ld", C.c_int64), ("weight_ld", C.c_int64),
                 ("dhidden_ld", C.c_int64), ("dweight_ld", C.c_int64), ("n_rows", C.c_int64),
                 ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("dweight_f32", C.c_int32),
-                ("accumulate", C.c_int32), ("cta_group", C.c_int32), ("dhidden_ws", C.c_void_p)]
+                ("accumulate", C.c_int32), ("cta_group", C.c_int32), ("dhidden_ws", C.c_void_p),
+                ("dweight_peers", C.c_void_p * 8), ("n_peers", C.c_int32)]
 
 
 class AdamWArgs(C.Structure):
@@ -109,6 +111,9 @@ def load() -> C.CDLL:
     lib.clear_param_l1l0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.clear_param_l1_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.clear_grad_scale.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.clear_head_dweight_slab.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.clear_dweight_allgather.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_float, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError here = the .so is stale / does not match include/clear_b200.h
     if lib.clear_abi_version() != 1:

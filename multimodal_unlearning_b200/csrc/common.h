@@ -35,8 +35,13 @@ struct GemmOperand {
   int64_t ld;  // leading dimension in elements of the row-major storage
   int major;   // 0: K-major  (storage [MN, K]);  1: MN-major (storage [K, MN])
 };
+// peer_d / n_peers: optional output buffers of the data-parallel peers (same shape and ldd as d; d itself may be one of
+// them): M tiles are reduce-added into the buffer of their owner rank (see PeerMaps in gemm_sm100.cuh).
 int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
-                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits = 1);
+                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits = 1,
+                     void* const* peer_d = nullptr, int n_peers = 0);
+// Rows [row0, row1) of an [m, *] output that rank `rank` of `n_peers` owns under that sharding.
+void gemm_peer_rows(int cta_group, int m, int n_peers, int rank, int* row0, int* row1);
 // Number of K splits (1..4) that best fills the last wave of CTA groups for this problem.
 int gemm_pick_k_splits(int cta_group, int m, int n, int k);
 

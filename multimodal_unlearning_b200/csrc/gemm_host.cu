@@ -92,9 +92,32 @@ static int make_output_map(CUtensorMap* tm, void* d, int d_is_f32, int64_t ldd, 
   return 0;
 }
 
+// Work counters of the dynamic tile scheduler: a ring of device words, one per launch in flight (launches on different
+// streams may overlap), allocated once per device on first use — the library's only device allocation — and zeroed on
+// the launching stream right before the kernel.
+static int next_work_counter(cudaStream_t stream, unsigned int** out) {
+  constexpr int kRing = 1024;
+  constexpr int kMaxDevices = 64;
+  static unsigned int* ring[kMaxDevices] = {};
+  static unsigned int cursor[kMaxDevices] = {};
+  static std::mutex mu;
+  int dev = 0;
+  CLEAR_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(CLEAR_ERR_DEVICE, "device ordinal %d out of range", dev);
+  unsigned int* slot;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ring[dev]) CLEAR_CUDA_OK(cudaMalloc(&ring[dev], kRing * sizeof(unsigned int)));
+    slot = ring[dev] + (cursor[dev]++ % kRing);
+  }
+  CLEAR_CUDA_OK(cudaMemsetAsync(slot, 0, sizeof(unsigned int), stream));
+  *out = slot;
+  return 0;
+}
+
 template <int kCtaGroup, int kMajorA, int kMajorB, int kEpi>
-static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmParams& p,
-                          cudaStream_t stream) {
+static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PeerMaps& peers,
+                          const GemmParams& p, cudaStream_t stream) {
   using S = GemmShape<kCtaGroup>;
   auto kern = gemm_bf16_kernel<kCtaGroup, kMajorA, kMajorB, kEpi>;
   static bool configured = false;  // per template instantiation
@@ -119,7 +142,7 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CLEAR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, p));
+  CLEAR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, peers, p));
   return 0;
 }
 
@@ -141,8 +164,24 @@ int gemm_pick_k_splits(int cta_group, int m, int n, int k) {
   return best;
 }
 
+static int peer_mtiles(int cta_group, int m, int n_peers) {
+  const int m_tiles = (m + 128 * cta_group - 1) / (128 * cta_group);
+  return (m_tiles + n_peers - 1) / n_peers;
+}
+
+void gemm_peer_rows(int cta_group, int m, int n_peers, int rank, int* row0, int* row1) {
+  if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
+  const int per = peer_mtiles(cta_group, m, n_peers) * 128 * cta_group;
+  long long r0 = (long long)rank * per, r1 = (rank == n_peers - 1) ? m : r0 + per;
+  if (r0 > m) r0 = m;
+  if (r1 > m) r1 = m;
+  *row0 = (int)r0;
+  *row1 = (int)r1;
+}
+
 int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
-                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits) {
+                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits,
+                     void* const* peer_d, int n_peers) {
   if (!a.ptr || !b.ptr || !d) return fail(CLEAR_ERR_NULL, "gemm: null operand");
   if (m <= 0 || n <= 0 || k <= 0) return fail(CLEAR_ERR_SHAPE, "gemm: non-positive dims m=%d n=%d k=%d", m, n, k);
   if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
@@ -167,6 +206,19 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
   if ((rc = make_operand_map(&tmA, a, m, k, 128))) return rc;
   if ((rc = make_operand_map(&tmB, b, n, k, 256 / cta_group))) return rc;
   if ((rc = make_output_map(&tmD, d, d_is_f32, ldd, m, n))) return rc;
+  static PeerMaps no_peers = {};
+  PeerMaps peer_maps_storage;
+  const PeerMaps* peers = &no_peers;
+  if (n_peers > 0) {
+    if (n_peers > kMaxPeers || !peer_d) return fail(CLEAR_ERR_SHAPE, "gemm: 1 <= n_peers <= %d with a pointer table required", kMaxPeers);
+    if (lse_part || k_splits > 1) return fail(CLEAR_ERR_KIND, "gemm: the peer-sharded epilogue excludes lse_part and split-K");
+    for (int r = 0; r < n_peers; ++r) {
+      if (!peer_d[r] || (reinterpret_cast<uintptr_t>(peer_d[r]) & 15)) return fail(CLEAR_ERR_ALIGN, "gemm: peer buffer %d is NULL or misaligned", r);
+      if ((rc = make_output_map(&peer_maps_storage.tm[r], peer_d[r], d_is_f32, ldd, m, n))) return rc;
+    }
+    for (int r = n_peers; r < kMaxPeers; ++r) peer_maps_storage.tm[r] = peer_maps_storage.tm[0];
+    peers = &peer_maps_storage;
+  }
 
   GemmParams p;
   p.M = m; p.N = n; p.K = k;
@@ -182,11 +234,14 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
     p.k_splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty item
   }
   p.lse_part = reinterpret_cast<float2*>(lse_part);
+  if ((rc = next_work_counter(stream, &p.work_counter))) return rc;
+  p.n_peers = n_peers;
+  p.mtiles_per_peer = n_peers > 0 ? peer_mtiles(cta_group, m, n_peers) : 1;
 
   const int epi = d_is_f32 ? kEpiStoreF32 : (lse_part ? kEpiStoreBF16Lse : kEpiStoreBF16);
 #define CLEAR_DISPATCH(CG, MA, MB, EPI)                                                     \
   if (cta_group == CG && a.major == MA && b.major == MB && epi == EPI)                      \
-    return launch_variant<CG, MA, MB, EPI>(tmA, tmB, tmD, p, stream);
+    return launch_variant<CG, MA, MB, EPI>(tmA, tmB, tmD, *peers, p, stream);
   CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16)
   CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16Lse)
   CLEAR_DISPATCH(1, kMajorK, kMajorMN, kEpiStoreBF16)

@@ -541,6 +541,42 @@ __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* src,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// All-gather half of the fused dW all-reduce: this rank's reduced slab -> every rank's buffer.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
+struct PeerPtrs {
+  __nv_bfloat16* p[8];
+};
+
+__global__ void __launch_bounds__(256) dweight_allgather_kernel(const __nv_bfloat16* local, __nv_bfloat16* mc, PeerPtrs peers,
+                                                                int n_peers, int64_t ld, int row0, int vec_per_row,
+                                                                int64_t nvec, float scale) {
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) {
+    const int64_t r = i / vec_per_row;
+    const int64_t off = (row0 + r) * ld + ((i - r * vec_per_row) << 3);
+    uint4 raw = *reinterpret_cast<const uint4*>(local + off);
+    if (scale != 1.f) {
+      float x[8];
+      unpack8(raw, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] *= scale;
+      raw = pack8(x);
+    }
+    if (mc) {
+      multimem_st_v4(mc + off, raw);
+    } else {
+      for (int p = 0; p < n_peers; ++p) *reinterpret_cast<uint4*>(peers.p[p] + off) = raw;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // small reductions
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) count_valid_kernel(const int64_t* labels, int64_t n, float* inv_count) {
@@ -737,15 +773,55 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
       if (rc) return rc;
     }
   }
-  if (a->dweight) {
+  if (a->dweight || a->n_peers > 0) {
     if (!a->hidden) return fail(CLEAR_ERR_NULL, "clear_head_backward: dweight requested but hidden is NULL");
+    if (a->n_peers < 0 || a->n_peers > 8) return fail(CLEAR_ERR_SHAPE, "clear_head_backward: 0 <= n_peers <= 8");
+    if (a->n_peers > 0 && a->dweight_f32) return fail(CLEAR_ERR_KIND, "clear_head_backward: the peer reduce-scatter accumulates in bf16");
     // dW[v, h] = sum_n dZ[n, v] H[n, h]: both operands read MN-major (K = rows).
     GemmOperand A{a->dlogits, a->dlogits_ld, kMajorMN};
     GemmOperand B{a->hidden, a->hidden_ld, kMajorMN};
-    rc = launch_gemm_bf16(a->cta_group, A, B, a->dweight, a->dweight_f32, a->dweight_ld, a->vocab, a->hidden_dim,
-                          (int)a->n_rows, nullptr, a->accumulate, /*raster_m_fast=*/0, stream);
+    void* d = a->dweight ? a->dweight : a->dweight_peers[0];
+    rc = launch_gemm_bf16(a->cta_group, A, B, d, a->dweight_f32, a->dweight_ld, a->vocab, a->hidden_dim,
+                          (int)a->n_rows, nullptr, a->accumulate, /*raster_m_fast=*/0, stream, 1,
+                          a->n_peers > 0 ? a->dweight_peers : nullptr, a->n_peers);
     if (rc) return rc;
   }
+  return 0;
+}
+
+int clear_head_dweight_slab(int32_t vocab, int32_t n_peers, int32_t rank, int32_t cta_group, int32_t* row0, int32_t* row1) {
+  if (!row0 || !row1) return fail(CLEAR_ERR_NULL, "clear_head_dweight_slab: null pointer");
+  if (vocab <= 0 || n_peers <= 0 || n_peers > 8 || rank < 0 || rank >= n_peers) return fail(CLEAR_ERR_SHAPE, "clear_head_dweight_slab: bad sizes");
+  int r0, r1;
+  gemm_peer_rows(cta_group, vocab, n_peers, rank, &r0, &r1);
+  *row0 = r0;
+  *row1 = r1;
+  return 0;
+}
+
+int clear_dweight_allgather(const void* local_buf, void* multicast_buf, void* const* peer_bufs, int32_t n_peers, int64_t ld,
+                            int32_t row0, int32_t row1, int32_t hidden_dim, float scale, void* stream) {
+  if (!local_buf || (!multicast_buf && !peer_bufs)) return fail(CLEAR_ERR_NULL, "clear_dweight_allgather: null pointer");
+  if (n_peers <= 0 || n_peers > 8 || row0 < 0 || row1 < row0 || hidden_dim <= 0 || (hidden_dim & 7) || (ld & 7) || ld < hidden_dim)
+    return fail(CLEAR_ERR_SHAPE, "clear_dweight_allgather: bad sizes");
+  if ((reinterpret_cast<uintptr_t>(local_buf) | reinterpret_cast<uintptr_t>(multicast_buf)) & 15)
+    return fail(CLEAR_ERR_ALIGN, "clear_dweight_allgather: buffers must be 16-byte aligned");
+  if (row1 == row0) return 0;
+  PeerPtrs pp = {};
+  if (!multicast_buf)
+    for (int p = 0; p < n_peers; ++p) {
+      if (!peer_bufs[p] || (reinterpret_cast<uintptr_t>(peer_bufs[p]) & 15)) return fail(CLEAR_ERR_ALIGN, "clear_dweight_allgather: peer buffer %d", p);
+      pp.p[p] = static_cast<__nv_bfloat16*>(peer_bufs[p]);
+    }
+  const int vec_per_row = hidden_dim >> 3;
+  const int64_t nvec = (int64_t)(row1 - row0) * vec_per_row;
+  // a few CTAs are enough to saturate NVLink; keep the SM footprint small so the overlapped compute is not disturbed
+  int64_t blocks = (nvec + 255) / 256;
+  if (blocks > 32) blocks = 32;
+  dweight_allgather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(local_buf), static_cast<__nv_bfloat16*>(multicast_buf), pp, n_peers, ld, row0, vec_per_row,
+      nvec, scale);
+  CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }
 

@@ -77,17 +77,57 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
+// try_wait that acquires at cluster scope: for data another CTA of the cluster stored into this CTA's shared memory
+// (st.shared::cluster) before its mbarrier.arrive.release.cluster.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// 32-bit store into the shared memory of CTA `cta` of the cluster, at the same offset as local address `addr`.
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t addr, uint32_t cta, uint32_t value) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 raddr;\n"
+      "mapa.shared::cluster.u32 raddr, %0, %1;\n"
+      "st.shared::cluster.u32 [raddr], %2;\n"
+      "}" ::"r"(addr),
+      "r"(cta), "r"(value)
+      : "memory");
+}
+
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t value) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a
 // hung GPU.  The bound is wall-clock (%globaltimer), checked every 4096 failed probes, so the fast
 // path is the bare try_wait loop.
 #ifndef CLEAR_MBAR_TIMEOUT_NS
 #define CLEAR_MBAR_TIMEOUT_NS 4000000000ull
 #endif
+template <bool kClusterAcquire = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  auto probe = [&]() { return kClusterAcquire ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity); };
+  if (probe()) return;
   uint32_t spins = 0;
   uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!probe()) {
     if ((++spins & 4095u) == 0) {
       uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;

@@ -140,24 +140,34 @@ def rowloss(kind: int, logits: torch.Tensor, lse_part: torch.Tensor, loss_rows: 
 
 def backward(dlogits: torch.Tensor, vocab: int, hidden: torch.Tensor, weight: torch.Tensor,
              dhidden: torch.Tensor | None, dweight: torch.Tensor | None, accumulate: bool = False,
-             cta_group: int = 0, dhidden_ws: torch.Tensor | None = None) -> None:
+             cta_group: int = 0, dhidden_ws: torch.Tensor | None = None, dweight_peers=None) -> None:
+    """dweight_peers: optional list of the data-parallel ranks' accumulation-buffer pointers (distributed.
+    FusedGradReducer): the dW contraction reduce-adds each output tile into its owner's buffer (fused reduce-scatter)."""
     lib = _lib.load()
     a = _lib.BackwardArgs(dlogits=dlogits.data_ptr(), hidden=hidden.data_ptr(), weight=weight.data_ptr(),
                           dhidden=_ptr(dhidden), dweight=_ptr(dweight), dlogits_ld=dlogits.stride(0),
                           hidden_ld=hidden.stride(0), weight_ld=weight.stride(0),
                           dhidden_ld=dhidden.stride(0) if dhidden is not None else 0,
-                          dweight_ld=dweight.stride(0) if dweight is not None else 0, n_rows=dlogits.shape[0],
+                          dweight_ld=dweight.stride(0) if dweight is not None else hidden.shape[1], n_rows=dlogits.shape[0],
                           hidden_dim=hidden.shape[1], vocab=vocab,
                           dweight_f32=int(dweight is not None and dweight.dtype == torch.float32),
                           accumulate=int(accumulate), cta_group=cta_group, dhidden_ws=_ptr(dhidden_ws))
+    if dweight_peers:
+        if dweight is not None:
+            raise RuntimeError("backward: pass dweight or dweight_peers, not both")
+        a.n_peers = len(dweight_peers)
+        for r, ptr in enumerate(dweight_peers):
+            a.dweight_peers[r] = ptr
+        dweight = True  # a dW contraction is requested (its output goes to the peers' buffers)
     if StageTimer.active is None or dhidden is None or dweight is None:
         tag = "gemm_dweight" if dhidden is None else ("gemm_dhidden" if dweight is None else "gemm_backward")
         _timed(tag, lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
         return
     # timed runs issue the two contractions separately so that each launch gets its own events
-    a.dweight = None
+    n_peers, dw_ptr = a.n_peers, a.dweight
+    a.dweight, a.n_peers = None, 0
     _timed("gemm_dhidden", lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
-    a.dweight, a.dhidden = dweight.data_ptr(), None
+    a.dweight, a.n_peers, a.dhidden = dw_ptr, n_peers, None
     _timed("gemm_dweight", lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
 
 
@@ -224,7 +234,7 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
                       reduction: str = "reference", n_seqs: int | None = None,
                       row_weight: torch.Tensor | None = None, need_dhidden: bool = True, need_dweight: bool = True,
                       dweight_accum: torch.Tensor | None = None, block_rows: int | None = None,
-                      cta_group: int = 0, overlap: bool = False) -> HeadResult:
+                      cta_group: int = 0, overlap: bool = False, dweight_target=None) -> HeadResult:
     """One head invocation: loss = coef * norm * sum_i term_i, plus d loss/d hidden and d loss/d weight.
 
     hidden [N, H] bf16, weight [V, H] bf16; labels [N] int64 ALREADY SHIFTED (see shift_labels) for CE;
@@ -233,6 +243,9 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     dweight_accum: optional fp32 [V, H] buffer; dW is ADDED into it (gradient accumulation across
     splits / micro-batches happens in fp32 inside the contraction's epilogue) and returned as is.
     need_dhidden = need_dweight = False gives the forward-only mode (no dlogits are written).
+    dweight_target: a `distributed.FusedGradReducer.begin()` target — dW is not returned; every tile of it is
+    reduce-added into the owner rank's buffer by the contraction itself (HeadResult.dweight is None; the reduced,
+    averaged gradient comes from `reducer.finish(target)`).
     overlap: issue the contractions and the row passes on two streams (see the staging comment below).  Off
     by default: under the 1 kW power cap the step is energy-bound and the overlap measured no gain on B200.
     """
@@ -302,7 +315,14 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     loss_rows = torch.empty(n, dtype=torch.float32, device=dev)
     dhidden = torch.empty_like(hidden) if need_dhidden else None
     dweight = None
-    if need_dweight:
+    peers = None
+    if dweight_target is not None:
+        if not need_dweight or dweight_accum is not None:
+            raise RuntimeError("dweight_target needs need_dweight=True and excludes dweight_accum")
+        if tuple(dweight_target.shape) != tuple(weight.shape):
+            raise RuntimeError("dweight_target was created for a different weight shape")
+        peers = dweight_target.peer_ptrs
+    elif need_dweight:
         if dweight_accum is not None:
             if dweight_accum.dtype != torch.float32 or dweight_accum.shape != weight.shape or not dweight_accum.is_contiguous():
                 raise RuntimeError("dweight_accum must be a contiguous fp32 [V, H] tensor")
@@ -345,9 +365,11 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
 
     def do_backward(b):
         r0, r1, zb, _ = block(b)
+        if peers is not None and b == 0:
+            torch.cuda.current_stream().wait_event(dweight_target.ready)  # owners zeroed their slabs, all ranks agreed
         backward(zb, v, hidden[r0:r1], weight, dhidden[r0:r1] if need_dhidden else None,
-                 dweight if need_dweight else None, accumulate=(dweight_accum is not None) or b > 0, cta_group=cta_group,
-                 dhidden_ws=dh_ws)
+                 dweight if (need_dweight and peers is None) else None, accumulate=(dweight_accum is not None) or b > 0,
+                 cta_group=cta_group, dhidden_ws=dh_ws, dweight_peers=peers)
 
     launches += n_blocks * (2 + int(needs_ref) + (int(need_dhidden) + int(need_dweight) if write_grad else 0))
     if not pipelined:
@@ -393,7 +415,7 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         seq_loss = torch.empty(n_seqs, dtype=torch.float32, device=dev)
         reduce_sequences(loss_rows, n_seqs, seq_loss)
         launches += 1
-    if need_dweight and dweight_accum is None and dweight.dtype != torch.bfloat16:
+    if need_dweight and peers is None and dweight_accum is None and dweight.dtype != torch.bfloat16:
         dweight = dweight.to(torch.bfloat16)
     del lib
     return HeadResult(loss, seq_loss, dhidden, dweight, loss_rows, launches)

@@ -43,6 +43,7 @@ def test_struct_layouts_match_header_field_order():
             first = names[0].split()[-1].lstrip("*")
             fields.append(first)
             fields += [n.strip().lstrip("*") for n in names[1:]]
+        fields = [re.sub(r"\[\d+\]$", "", f) for f in fields]   # `void* dweight_peers[8]` -> dweight_peers
         assert [f[0] for f in cls._fields_] == fields, cname
 
 
@@ -85,3 +86,21 @@ def test_product_never_imports_the_oracle():
     for f in pkg.glob("*.py"):
         src = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_dweight_slabs_partition_the_vocabulary():
+    """Owner slabs of the fused reduce-scatter: contiguous, whole 256-row output tiles, cover [0, V) exactly."""
+    import ctypes as C
+    from multimodal_unlearning_b200 import _lib
+    lib = _lib.load()
+    for vocab in (32064, 32000, 13, 256, 257):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for rank in range(world):
+                r0, r1 = C.c_int32(), C.c_int32()
+                _lib.check(lib.clear_head_dweight_slab(vocab, world, rank, 0, C.byref(r0), C.byref(r1)), "slab")
+                assert r0.value == min(prev, vocab) and r0.value <= r1.value <= vocab
+                assert r0.value % 256 == 0 or r0.value == vocab
+                prev = r1.value
+            assert prev == vocab
+    assert lib.clear_head_dweight_slab(100, 9, 0, 0, C.byref(C.c_int32()), C.byref(C.c_int32())) < 0

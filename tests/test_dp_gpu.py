@@ -38,6 +38,29 @@ def _worker(rank, world, port, out_dir):
     # per-rank loss is the mean over its own rows; dH of the full batch carries 1/(R n) instead of 1/n
     relh = ((res.dhidden.float() / world - full.dhidden[sl].float()).norm() / full.dhidden[sl].float().norm()).item()
     assert relh < 2e-2, relh
+    # the same mean, fused into the contraction: reduce-scatter in the dW epilogue over NVLink + multicast all-gather
+    fused = D.FusedGradReducer((v, h), dev, average=True)
+    nccl_dw = res.dweight.clone()
+    for it in range(3):                                        # three steps: both buffers and a buffer reuse
+        tgt = fused.begin()
+        r2 = head.head_loss_fwd_bwd(hid[sl], wgt, KIND_KL_FWD, ref_hidden=ref[sl], ref_weight=wgt, dweight_target=tgt,
+                                    block_rows=256 if it == 1 else None)   # it == 1: two row blocks accumulate at the owners
+        assert r2.dweight is None
+        ev, dw = fused.finish(tgt)
+        torch.cuda.current_stream().wait_event(ev)
+        torch.cuda.synchronize()
+        rel = ((dw.float() - full.dweight.float()).norm() / full.dweight.float().norm()).item()
+        assert rel < 2e-2, (it, rel)
+        rel2 = ((dw.float() - nccl_dw.float()).norm() / nccl_dw.float().norm()).item()
+        assert rel2 < 1e-2, (it, rel2)
+        # bit-identical on every rank
+        mine = dw.view(torch.int16).to(torch.int32).sum(dtype=torch.int64).reshape(1)
+        both = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        assert all(int(x) == int(mine) for x in both)
+        gathered = [torch.empty_like(dw) for _ in range(world)]
+        dist.all_gather(gathered, dw.contiguous())
+        assert all(torch.equal(gx, dw) for gx in gathered)
     losses = torch.stack([res.loss.reshape(())])
     dist.all_reduce(losses, op=dist.ReduceOp.AVG)
     assert abs(losses.item() - full.loss.item()) <= 1e-3 * abs(full.loss.item())
