@@ -36,6 +36,8 @@ struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles;  // in units of (128*cta_group) x 256
   int raster_m_fast;     // 1: consecutive tiles walk M first (A small / re-read from L2), 0: N first
+  int raster_group;      // tiles of the fast dimension per chunk: a chunk is swept across the whole slow dimension before
+                         // the next chunk starts, so that the chunk's operand stays in L2 (see pick_raster in gemm_host.cu)
   int reduce_add;        // accumulate into D instead of overwriting (TMA reduce-add; bf16 D rounds after each add)
   int k_splits;          // > 1: each output tile is cut into k_splits work items along K (fp32 reduce-add epilogue)
   int kb_per_split;      // K blocks (of 64) per work item
@@ -159,6 +161,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int num_kb_total = (p.K + S::BK - 1) / S::BK;
 
+  // Work item -> output tile.  Chunks of `raster_group` tiles along the fast dimension, each swept across the slow one.
+  auto tile_coords = [&](int t, int& mt, int& nt) {
+    const int fast_tiles = p.raster_m_fast ? p.m_tiles : p.n_tiles;
+    const int slow_tiles = p.raster_m_fast ? p.n_tiles : p.m_tiles;
+    const int per_chunk = p.raster_group * slow_tiles;
+    const int c = t / per_chunk;
+    const int r = t - c * per_chunk;
+    const int g = min(p.raster_group, fast_tiles - c * p.raster_group);
+    const int slow = r / g;
+    const int fast = c * p.raster_group + (r - slow * g);
+    mt = p.raster_m_fast ? fast : slow;
+    nt = p.raster_m_fast ? slow : fast;
+  };
+
   // Reader side of the scheduler ring.  Every reader consumes every slot in order, the end-of-work item (>= num_tiles)
   // included.  Called by one thread; the epilogue warps broadcast the result with a shuffle.
   auto sched_read = [&](uint32_t& slot, uint32_t& sphase) -> int {
@@ -204,8 +220,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int t = w / p.k_splits;
         const int kb0 = (w % p.k_splits) * p.kb_per_split;
         const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-        const int mt = p.raster_m_fast ? (t % p.m_tiles) : (t / p.n_tiles);
-        const int nt = p.raster_m_fast ? (t / p.m_tiles) : (t % p.n_tiles);
+        int mt, nt;
+        tile_coords(t, mt, nt);
         const int m0 = (mt * kCtaGroup + (int)cta_rank) * S::BM;
         const int n0 = nt * S::BN + (int)cta_rank * S::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -289,8 +305,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w >= num_tiles) break;
       const int t = w / p.k_splits;
-      const int mt = p.raster_m_fast ? (t % p.m_tiles) : (t / p.n_tiles);
-      const int nt = p.raster_m_fast ? (t / p.m_tiles) : (t % p.n_tiles);
+      int mt, nt;
+      tile_coords(t, mt, nt);
       const int row0 = (mt * kCtaGroup + (int)cta_rank) * S::BM + (int)q * 32;
       const int col0 = nt * S::BN;
       // destination: this rank's D, or the buffer of the rank that owns these rows (always reduce-add there)

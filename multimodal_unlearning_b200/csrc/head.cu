@@ -630,7 +630,7 @@ int clear_head_project(const ClearProjectArgs* a, void* stream) {
   GemmOperand A{a->hidden, a->hidden_ld, kMajorK};
   GemmOperand B{a->weight, a->weight_ld, kMajorK};
   return launch_gemm_bf16(a->cta_group, A, B, a->logits, 0, a->logits_ld, (int)a->n_rows, a->vocab, a->hidden_dim,
-                          a->lse_part, 0, /*raster_m_fast=*/1, static_cast<cudaStream_t>(stream));
+                          a->lse_part, 0, /*raster: traffic model*/ -1, static_cast<cudaStream_t>(stream));
 }
 
 int clear_head_lse_partials(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
@@ -761,7 +761,7 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
       const size_t ws_elems = (size_t)a->n_rows * a->hidden_dim;
       CLEAR_CUDA_OK(cudaMemsetAsync(a->dhidden_ws, 0, ws_elems * sizeof(float), stream));
       rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden_ws, 1, a->hidden_dim, (int)a->n_rows, a->hidden_dim, a->vocab,
-                            nullptr, /*reduce_add=*/1, /*raster_m_fast=*/0, stream, splits);
+                            nullptr, /*reduce_add=*/1, /*raster: traffic model*/ -1, stream, splits);
       if (rc) return rc;
       const int64_t nvec = (int64_t)a->n_rows * (a->hidden_dim / 8);
       f32_to_bf16_rows_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, stream>>>(
@@ -769,7 +769,7 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
       CLEAR_CUDA_OK(cudaGetLastError());
     } else {
       rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden, 0, a->dhidden_ld, (int)a->n_rows, a->hidden_dim, a->vocab,
-                            nullptr, 0, /*raster_m_fast=*/0, stream);
+                            nullptr, 0, /*raster: traffic model*/ -1, stream);
       if (rc) return rc;
     }
   }
@@ -782,7 +782,7 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
     GemmOperand B{a->hidden, a->hidden_ld, kMajorMN};
     void* d = a->dweight ? a->dweight : a->dweight_peers[0];
     rc = launch_gemm_bf16(a->cta_group, A, B, d, a->dweight_f32, a->dweight_ld, a->vocab, a->hidden_dim,
-                          (int)a->n_rows, nullptr, a->accumulate, /*raster_m_fast=*/0, stream, 1,
+                          (int)a->n_rows, nullptr, a->accumulate, /*raster: traffic model*/ -1, stream, 1,
                           a->n_peers > 0 ? a->dweight_peers : nullptr, a->n_peers);
     if (rc) return rc;
   }

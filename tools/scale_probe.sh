@@ -9,13 +9,13 @@ run() {
 import json
 try:
     d = json.loads(open("gpurun_out/scale_$tag.json").read().strip().splitlines()[-1])
-    print("$tag", "ms/step", round(d["ms_per_step"], 3), "tok/s", round(d["value"]), "gemm ms", round(d["roofline"]["kernel_ms_per_step"], 3), "rowloss", round(d["roofline"]["rowloss_ms_per_step"], 3), d["clocks"])
+    print("$tag", "ms/step", round(d["ms_per_step"], 3), "tok/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "gemm ms", round(d["roofline"]["kernel_ms_per_step"], 3), "rowloss", round(d["roofline"]["rowloss_ms_per_step"], 3), d["clocks"])
 except Exception as e:
     print("$tag failed", e)
+    print(open("gpurun_out/scale_$tag.err").read()[-1500:])
 PY
 }
-EXTRA="" run default A=1
+EXTRA="--allreduce fused" run fused A=1
 EXTRA="--no-allreduce" run noallreduce A=1
-EXTRA="" run maxctas4 NCCL_MAX_CTAS=4
-EXTRA="" run maxctas16 NCCL_MAX_CTAS=16
-EXTRA="" run maxctas8 NCCL_MAX_CTAS=8
+EXTRA="--allreduce nccl" run nccl A=1
+EXTRA="--allreduce fused" run fused2 A=1
