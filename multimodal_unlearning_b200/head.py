@@ -442,6 +442,17 @@ def _ref_lse(ref_logits: torch.Tensor, lse_part: torch.Tensor, vocab: int) -> No
 # --------------------------------------------------------------------------------------------------
 # autograd boundary
 # --------------------------------------------------------------------------------------------------
+_DW_REDUCER = None
+
+
+def set_dweight_reducer(reducer) -> None:
+    """Route d loss / d lm_head.weight of every differentiable head invocation through a
+    `distributed.FusedGradReducer` (mean over the data-parallel ranks, fused into the contraction).  The parameter
+    must then be excluded from DDP's own reducer (`trainer.enable_fused_head_allreduce` does both).  None = off."""
+    global _DW_REDUCER
+    _DW_REDUCER = reducer
+
+
 class _FusedHeadLoss(torch.autograd.Function):
     """loss = f(hidden, weight).  Forward runs the fused forward+backward (dlogits exist only inside the
     staging block), backward scales the stored dH / dW by the incoming scalar gradient."""
@@ -457,12 +468,19 @@ class _FusedHeadLoss(torch.autograd.Function):
         rh = ref_hidden.reshape(-1, shape[-1]).to(torch.bfloat16).contiguous() if ref_hidden is not None else None
         rw = ref_weight.to(torch.bfloat16).contiguous() if ref_weight is not None else None
         rl = ref_logits.reshape(-1, ref_logits.shape[-1]).to(torch.bfloat16).contiguous() if ref_logits is not None else None
+        reducer = _DW_REDUCER if (ctx.needs_input_grad[1] and _DW_REDUCER is not None
+                                  and tuple(_DW_REDUCER.shape) == tuple(wb.shape)) else None
+        target = reducer.begin() if reducer is not None else None
         res = head_loss_fwd_bwd(hb, wb, kind, labels=labels, ref_hidden=rh, ref_weight=rw, ref_logits=rl, beta=beta,
                                 coef=coef, reduction=reduction, n_seqs=n_seqs, row_weight=row_weight,
                                 need_dhidden=ctx.needs_input_grad[0], need_dweight=ctx.needs_input_grad[1],
-                                block_rows=block_rows)
+                                block_rows=block_rows, dweight_target=target)
         dh = res.dhidden.reshape(shape) if res.dhidden is not None else None
         dw = res.dweight
+        if reducer is not None:
+            done, buf = reducer.finish(target)
+            torch.cuda.current_stream().wait_event(done)
+            dw = buf.clone()  # the symmetric buffer is reused two invocations later; autograd may hold dW longer
         if cast:
             dh = dh.to(hidden.dtype) if dh is not None else None
             dw = dw.to(weight.dtype) if dw is not None else None

@@ -232,6 +232,33 @@ class _Recipes:
         return surrogate + (value - surrogate).detach()
 
 
+def enable_fused_head_allreduce(model, group=None):
+    """Data-parallel runs (one process per GPU, one NVSwitch box): average d loss / d lm_head.weight with the all-reduce
+    that is fused into the dW contraction (distributed.FusedGradReducer) instead of DDP's bucketed NCCL all-reduce.
+    Call once, on the bare model, BEFORE it is wrapped by DistributedDataParallel (HF Trainer / accelerate wrap it
+    inside `train()`): the parameter is put on DDP's ignore list and every head invocation then delivers the mean
+    gradient itself.  Returns the reducer (None when there is a single rank)."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from . import distributed as D
+
+    if not dist.is_initialized() or dist.get_world_size(group) < 2:
+        return None
+    base = _unwrap(model)
+    if getattr(getattr(base, "config", None), "tie_word_embeddings", False):
+        raise RuntimeError("lm_head.weight is tied to the input embedding: its gradient has a second contribution that "
+                           "DDP must reduce; the fused head all-reduce cannot take the parameter over")
+    lm_head = _locate_head(model)[2]
+    names = [n for n, p in model.named_parameters() if p is lm_head.weight]
+    if not names:
+        raise RuntimeError("lm_head.weight is not a parameter of the model")
+    DDP._set_params_and_buffers_to_ignore_for_model(model, names)
+    reducer = D.FusedGradReducer(tuple(lm_head.weight.shape), lm_head.weight.device, group=group, average=True)
+    head.set_dweight_reducer(reducer)
+    return reducer
+
+
 def _teacher_cache(self) -> TeacherCache | None:
     """Extension: `teacher_cache_gb=<float>` ctor kwarg (or a `teacher_cache` attribute) enables
     replay of the frozen teacher's hidden states; absent / 0 = the reference's behaviour (teacher forward every step)."""

@@ -78,3 +78,61 @@ def test_two_rank_nccl_dp_equivalence(tmp_path):
     s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    """The nlp trainer's compute_loss under DistributedDataParallel, twice: stock DDP (NCCL buckets reduce every gradient)
+    and with lm_head.weight handed to the fused head all-reduce.  Same gradients on every parameter."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import copy
+    import types
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from multimodal_unlearning_b200 import distributed as D
+    from multimodal_unlearning_b200 import head
+    from multimodal_unlearning_b200 import trainer as T
+    from oracle import ref_harness as RH
+    D.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    base = RH.tiny_llama(0).to(dev).to(torch.bfloat16)
+    teacher = RH.perturbed_copy(RH.tiny_llama(0), 5).to(dev).to(torch.bfloat16)
+    inputs = [RH.nlp_triple(2, 64, 100 + rank), RH.nlp_triple(2, 64, 200 + rank), RH.nlp_triple(2, 64, 300 + rank)]
+    fake = types.SimpleNamespace(loss_type="KL", oracle_model=teacher, loss_beta=1.0, l1_lambda=0.0, l0_lambda=0.0)
+
+    def run(fused):
+        model = copy.deepcopy(base)
+        model.train()
+        reducer = T.enable_fused_head_allreduce(model) if fused else None
+        assert (reducer is not None) == fused
+        ddp = DDP(model, device_ids=[rank])
+        loss = T.CustomTrainerForgetting.compute_loss(fake, ddp, inputs)
+        loss.backward()
+        torch.cuda.synchronize()
+        head.set_dweight_reducer(None)
+        return {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
+
+    want = run(False)
+    got = run(True)
+    for n in want:
+        rel = ((got[n] - want[n]).norm() / want[n].norm().clamp_min(1e-30)).item()
+        assert rel < 3e-2, (n, rel)
+    # and the fused gradient is identical on both ranks
+    g = got["lm_head.weight"].contiguous()
+    both = [torch.empty_like(g) for _ in range(world)]
+    dist.all_gather(both, g)
+    assert torch.equal(both[0], both[1])
+    (Path(out_dir) / f"ddp_ok{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_trainer_under_ddp_with_fused_head_allreduce(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ddp_ok0").exists() and (tmp_path / "ddp_ok1").exists()
