@@ -161,12 +161,19 @@ __global__ void __launch_bounds__(kThreads) rowloss_ce_kernel(const RowLossParam
     if (threadIdx.x == 0) a.loss_rows[row] = 0.f;
     return;
   }
+  // the first two vectors of every thread are in flight while the row statistics are merged; one more is requested
+  // per iteration (register double-buffering)
+  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+  if ((int)threadIdx.x < nvec) n0 = reinterpret_cast<const uint4*>(z)[threadIdx.x];
+  if ((int)threadIdx.x + kThreads < nvec) n1 = reinterpret_cast<const uint4*>(z)[threadIdx.x + kThreads];
   const float lse = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
   const float nl2 = -lse * kLog2e;
   const int yv = (int)(y >> 3), yj = (int)(y & 7);
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
-    const uint4 raw = reinterpret_cast<const uint4*>(z)[v];
+    const uint4 raw = n0;
+    n0 = n1;
+    if (v + 2 * kThreads < nvec) n1 = reinterpret_cast<const uint4*>(z)[v + 2 * kThreads];
     float x[8];
     unpack8(raw, x);
     if (v == yv) a.loss_rows[row] = (lse - x[yj]) * w;
@@ -190,19 +197,30 @@ __global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossPa
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
   const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
+  const int nvec = (int)(a.ld >> 3);
+  const int nfull = a.vocab >> 3;
+  const int ref_nvec = (int)(a.ref_ld >> 3);  // a materialised teacher may be narrower than the staging buffer
+  auto ld_ref = [&](int v) { return v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0); };
+  // first vector pair in flight while the row statistics are merged; register double-buffering afterwards
+  uint4 nx = make_uint4(0, 0, 0, 0), nr = nx;
+  if ((int)threadIdx.x < nvec) {
+    nx = reinterpret_cast<const uint4*>(z)[threadIdx.x];
+    nr = ld_ref(threadIdx.x);
+  }
   float lse_s, lse_t;
   merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, lse_s, lse_t);
   const float nls2 = -lse_s * kLog2e, nlt2 = -lse_t * kLog2e, dlse = lse_s - lse_t;
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
-  const int nvec = (int)(a.ld >> 3);
-  const int nfull = a.vocab >> 3;
-  const int ref_nvec = (int)(a.ref_ld >> 3);  // a materialised teacher may be narrower than the staging buffer
   float acc = 0.f;
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8], r[8];
-    unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-    unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
+    unpack8(nx, x);
+    unpack8(nr, r);
+    if (v + kThreads < nvec) {
+      nx = reinterpret_cast<const uint4*>(z)[v + kThreads];
+      nr = ld_ref(v + kThreads);
+    }
     if (v < nfull) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
