@@ -214,7 +214,22 @@ def main():
     labels = torch.randint(0, V, (n,), generator=g, device=dev)  # unused by NPO; part of the batch a step receives
 
     fused = world > 1 and args.allreduce == "fused" and not args.no_allreduce
-    reducer = D.FusedGradReducer((V, H), dev, average=True) if fused else D.GradReducer(average=True)
+    fused_note = ""
+    if fused:
+        # symmetric memory needs peer access between all ranks' GPUs; every rank must take the same branch
+        ok = torch.ones(1, device=dev)
+        try:
+            reducer = D.FusedGradReducer((V, H), dev, average=True)
+        except Exception as e:  # noqa: BLE001 - reported in the JSON line, the bench falls back to the NCCL all-reduce
+            ok.zero_()
+            fused_note = f" (fused reducer unavailable: {type(e).__name__}: {str(e)[:120]})"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            fused = False
+            if not fused_note:
+                fused_note = " (fused reducer unavailable on another rank)"
+    if not fused:
+        reducer = D.GradReducer(average=True)
     dws = [None, None]
 
     def step(i, hid, rhid):
@@ -357,7 +372,7 @@ def main():
                        "dw_allreduce": ("SKIPPED (--no-allreduce diagnostic run)" if args.no_allreduce else
                                         ("fused: dW contraction epilogue TMA-reduce-adds tiles into the owner rank's buffer over NVLink "
                                          "(reduce-scatter), multimem.st all-gather through the NVSwitch multicast mapping, per step"
-                                         if fused else "NCCL all-reduce(avg) of bf16 dW per step, overlapped with the next step"))
+                                         if fused else "NCCL all-reduce(avg) of bf16 dW per step, overlapped with the next step" + fused_note))
                                        if world > 1 else "none (1 GPU)"},
             "e2e": {"value": tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

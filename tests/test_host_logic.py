@@ -141,3 +141,29 @@ def test_partition_units_is_balanced_and_deterministic():
     loads = [sum(sizes[i] for i in p) for p in parts]
     assert max(loads) <= 1.35 * (sum(sizes) / 4)
     assert parts == partition_units(sizes, 4)
+
+
+def test_teacher_cache_lru_eviction_and_keys():
+    from multimodal_unlearning_b200.teacher_cache import TeacherCache
+    dev = torch.device("cpu")   # keys and LRU bookkeeping are host logic; rows live wherever the caller puts them
+    c = TeacherCache(max_bytes=3 * 4 * 8 * 2)          # room for three [4, 8] bf16 rows
+    mk = lambda i: {"input_ids": torch.full((1, 4), i), "attention_mask": torch.ones(1, 4, dtype=torch.long)}
+    keys = [TeacherCache.sample_keys(mk(i), None)[0] for i in range(4)]
+    assert len(set(keys)) == 4 and all(len(k) == 16 for k in keys)
+    rows = [torch.full((1, 4, 8), float(i), dtype=torch.bfloat16, device=dev) for i in range(4)]
+    for i in range(3):
+        c.store([keys[i]], rows[i])
+    assert c.lookup([keys[0]]) is not None              # touch 0: 1 becomes least recently used
+    c.store([keys[3]], rows[3])
+    assert c.lookup([keys[1]]) is None and c.lookup([keys[0], keys[3]]).shape == (2, 4, 8)
+    assert c.stats()["bytes"] == 3 * 4 * 8 * 2
+    # attention mask and image bytes are part of the key
+    a = mk(7)
+    b = {**a, "attention_mask": torch.tensor([[0, 1, 1, 1]])}
+    assert TeacherCache.sample_keys(a, None) != TeacherCache.sample_keys(b, None)
+    img = {"input_ids": torch.tensor([[5, 9, 9, 2], [5, 1, 1, 2]]), "attention_mask": torch.ones(2, 4, dtype=torch.long),
+           "pixel_values": torch.zeros(1, 3, 2, 2)}
+    k0 = TeacherCache.sample_keys(img, image_token_id=9)
+    img2 = {**img, "pixel_values": torch.ones(1, 3, 2, 2)}
+    k1 = TeacherCache.sample_keys(img2, image_token_id=9)
+    assert k0[0] != k1[0] and k0[1] == k1[1]            # only the sample that owns the image changes
