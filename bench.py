@@ -266,7 +266,7 @@ def main():
     for i in range(args.warmup):
         res = step(i, hidden, ref_hidden)
     barrier()
-    launches_per_step = res.launches
+    launches_per_step = res.launches + (1 if fused else 0)   # + the all-gather kernel of the fused all-reduce
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if rank == 0:
