@@ -136,6 +136,36 @@ def test_rowloss_vs_closed_forms(kind, v):
     assert (z[:, v:] == 0).all(), "padding columns must be zeroed"
 
 
+@pytest.mark.parametrize("v", [13, 1003, 32064, 40000])
+def test_npo_beta_one_kernel(v):
+    """The shipped NPO recipe (loss_beta = 1, config/mm/forget.yaml:40) runs its own row kernel (batched reciprocal /
+    logarithm, s cached in shared memory): ragged vocabularies (13, 1003), the BASELINE vocabulary, and one wider than
+    the shared-memory cache and the single-round-trip statistics merge (40000 = 157 column tiles)."""
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h = 70, 128
+    hid, w, rh, rw, y = _inputs(n, h, v, 77, dev)
+    ld = (v + 63) // 64 * 64
+    nt = head.vtiles(v)
+    z = torch.zeros((n, ld), dtype=torch.bfloat16, device=dev)
+    zr = torch.zeros((n, ld), dtype=torch.bfloat16, device=dev)
+    part = torch.empty(n, nt, 2, dtype=torch.float32, device=dev)
+    rpart = torch.empty(n, nt, 2, dtype=torch.float32, device=dev)
+    head.project(hid.to(dev), w.to(dev), z, part)
+    head.project(rh.to(dev), rw.to(dev), zr, rpart)
+    want_rows, want_d = HO.rowloss(HO.KIND_NPO, z[:, :v].double().cpu(), zr[:, :v].double().cpu(), y, 1.0)
+    rows = torch.empty(n, dtype=torch.float32, device=dev)
+    before = z.clone()
+    head.rowloss(HO.KIND_NPO, z, part, rows, v, ref_logits=zr, ref_lse_part=rpart, beta=1.0, write_grad=False)
+    assert torch.equal(before, z)
+    assert (rows.double().cpu() - want_rows).abs().max().item() <= LOSS_RTOL * want_rows.abs().max().item()
+    head.rowloss(HO.KIND_NPO, z, part, rows, v, ref_logits=zr, ref_lse_part=rpart, beta=1.0, grad_scale=0.5, write_grad=True)
+    torch.cuda.synchronize()
+    assert (rows.double().cpu() - want_rows).abs().max().item() <= LOSS_RTOL * want_rows.abs().max().item()
+    _assert_grad(z[:, :v], 0.5 * want_d, f"dlogits NPO beta=1 v={v}")
+    assert (z[:, v:] == 0).all(), "padding columns must be zeroed"
+
+
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("shape", [(300, 136, 1000), (512, 128, 32000), (130, 256, 32064)])
 def test_fused_head_vs_oracle(kind, shape):
