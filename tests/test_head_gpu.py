@@ -484,3 +484,45 @@ def test_gemm_split_k_reduce_add(k_splits, layout):
     got = D[:, :n].cpu()
     assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
     assert (D[:, n:] == 0.5).all()
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("layout", ["k_k", "k_mn", "mn_mn"])
+@pytest.mark.parametrize("raster", [-1, 0, 1])
+def test_gemm_layouts_groups_and_tile_orders(cta_group, layout, raster):
+    """Every operand layout the head uses, on one CTA and on CTA pairs (the claimed-work ring is mirrored into the peer
+    CTA only in the paired case), under the three tile orders (traffic model, N-fast, M-fast).  Shapes leave ragged
+    edge tiles in both dimensions and more work items than CTA groups would get from one wave."""
+    import ctypes as C
+
+    from multimodal_unlearning_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    m, n, k = 2100, 5000, 200          # 9 x 20 (pairs) / 17 x 20 (single) output tiles
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    B = torch.randn(n, k, generator=g).to(torch.bfloat16)
+    pad = lambda x: (x + 63) // 64 * 64
+
+    def store(x, major):  # x is [mn, k]
+        if major == 0:
+            st = torch.zeros(x.shape[0], pad(k), dtype=torch.bfloat16)
+            st[:, :k] = x
+        else:
+            st = torch.zeros(k, pad(x.shape[0]), dtype=torch.bfloat16)
+            st[:, :x.shape[0]] = x.t()
+        return st.to(dev)
+
+    a_major, b_major = {"k_k": (0, 0), "k_mn": (0, 1), "mn_mn": (1, 1)}[layout]
+    a_st, b_st = store(A, a_major), store(B, b_major)
+    D = torch.full((m, pad(n)), 7.0, dtype=torch.bfloat16, device=dev)
+    args = _lib.GemmArgs(a=a_st.data_ptr(), b=b_st.data_ptr(), d=D.data_ptr(), lse_part=None, lda=a_st.stride(0),
+                         ldb=b_st.stride(0), ldd=D.stride(0), m=m, n=n, k=k, a_major=a_major, b_major=b_major, d_f32=0,
+                         accumulate=0, cta_group=cta_group, raster_m_fast=raster, k_splits=1)
+    for _ in range(2):   # twice: the second launch takes the next work counter of the ring
+        _lib.check(lib.clear_gemm_bf16(C.byref(args), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "clear_gemm_bf16")
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().t()
+    got = D[:, :n].float().cpu()
+    assert (got - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+    assert (D[:, n:] == 7.0).all(), "columns beyond N must not be written"
