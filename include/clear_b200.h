@@ -141,6 +141,17 @@ int clear_head_rowloss(const ClearRowLossArgs* args, void* stream);
 /* inv_count[0] = 1 / #{i : labels[i] != -100}   (inf when none: the reference's mean CE is NaN then) */
 int clear_head_count_valid(const int64_t* labels, int64_t n_rows, float* inv_count, void* stream);
 
+/* Row compaction for CE-type losses: rows whose (shifted) label is -100 contribute nothing to the loss, to dW or to
+ * their own dH (HF ForCausalLMLoss ignore_index; the reference still projects them and backpropagates zero rows —
+ * in CLEAR's batches the padding, the 576 image positions and the question).  row_index[0 .. *count) = ascending
+ * indices of the valid rows (device int32; row_index holds n_rows entries).  The caller reads *count and runs the head
+ * on the gathered rows; gather / scatter move rows of row_bytes (a multiple of 4) between strided buffers:
+ *   gather:  dst[i] = src[row_index[i]]       scatter: dst[row_index[i]] = src[i]       i < n_idx */
+int clear_head_compact_rows(const int64_t* labels, int64_t n_rows, int32_t* row_index, int32_t* count, void* stream);
+int clear_rows_gather(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx, int32_t row_bytes,
+                      void* dst, int64_t dst_ld_bytes, void* stream);
+int clear_rows_scatter(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx, int32_t row_bytes,
+                       void* dst, int64_t dst_ld_bytes, void* stream);
 /* out[0] (+)= scale * (scale_dev ? *scale_dev : 1) * sum_i loss_rows[i]   — deterministic single-block tree */
 int clear_head_reduce_rows(const float* loss_rows, int64_t n_rows, float scale, const float* scale_dev,
                            float* out, int accumulate, void* stream);

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "clear_saliency_histogram", "clear_saliency_select", "clear_saliency_chunk_elems", "clear_saliency_mask",
     "clear_masked_adamw", "clear_reduce_partials_elems", "clear_grad_sqnorm", "clear_clip_coef", "clear_param_l1l0",
     "clear_param_l1_grad", "clear_grad_scale", "clear_saliency_mask_bits", "clear_mask_pack", "clear_mask_unpack",
-    "clear_head_dweight_slab", "clear_dweight_allgather",
+    "clear_head_dweight_slab", "clear_dweight_allgather", "clear_head_compact_rows", "clear_rows_gather", "clear_rows_scatter",
 )
 
 
@@ -114,6 +114,9 @@ def load() -> C.CDLL:
     lib.clear_head_dweight_slab.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.clear_dweight_allgather.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int32,
                                             C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    lib.clear_head_compact_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.clear_rows_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.clear_rows_scatter.argtypes = lib.clear_rows_gather.argtypes
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError here = the .so is stale / does not match include/clear_b200.h
     if lib.clear_abi_version() != 1:

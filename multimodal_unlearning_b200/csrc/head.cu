@@ -559,6 +559,54 @@ __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* src,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Row compaction for CE-type losses.  HF's causal-LM CE ignores rows whose (shifted) label is -100 — in CLEAR's
+// multimodal batches that is the padding, the 576 image positions and the question, i.e. most rows — yet the reference
+// projects every position and lets autograd push zero rows through the backward GEMMs.  Ignored rows contribute nothing
+// to the loss, to dW, or to their own dH, so the head can run on the valid rows only: same loss, same gradients.
+//   compact_rows:  ascending indices of the valid rows + their count (single CTA, block scan; N <= 2^24)
+//   rows_gather:   dst[i, :] = src[idx[i], :]        rows_scatter: dst[idx[i], :] = src[i, :]     (row_bytes % 4 == 0)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compact_rows_kernel(const int64_t* labels, int64_t n, int32_t* row_index, int32_t* count) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int valid = (i < n && labels[i] != kIgnoreIndex) ? 1 : 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    const int before = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) wsum[warp] = __popc(ballot);
+    __syncthreads();
+    int wb = 0;
+    for (int w = 0; w < warp; ++w) wb += wsum[w];
+    if (valid) row_index[carry + wb + before] = (int32_t)i;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += wb + __popc(ballot);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(256) rows_move_kernel(const uint8_t* src, int64_t src_ld_bytes, const int32_t* row_index,
+                                                        int64_t n_idx, int row_bytes, uint8_t* dst, int64_t dst_ld_bytes) {
+  const int lanes_per_row = (row_bytes & 15) ? ((row_bytes + 3) >> 2) : (row_bytes >> 4);
+  const int64_t total = n_idx * lanes_per_row;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / lanes_per_row;
+    const int c = (int)(t - i * lanes_per_row);
+    const int64_t r = row_index[i];
+    const uint8_t* s = src + (kScatter ? i : r) * src_ld_bytes;
+    uint8_t* d = dst + (kScatter ? r : i) * dst_ld_bytes;
+    if (row_bytes & 15) reinterpret_cast<uint32_t*>(d)[c] = reinterpret_cast<const uint32_t*>(s)[c];
+    else reinterpret_cast<uint4*>(d)[c] = reinterpret_cast<const uint4*>(s)[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // All-gather half of the fused dW all-reduce: this rank's reduced slab -> every rank's buffer.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
@@ -733,6 +781,48 @@ int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
   }
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int clear_head_compact_rows(const int64_t* labels, int64_t n_rows, int32_t* row_index, int32_t* count, void* stream) {
+  if (!labels || !row_index || !count) return fail(CLEAR_ERR_NULL, "clear_head_compact_rows: null pointer");
+  if (n_rows <= 0 || n_rows > (1 << 24)) return fail(CLEAR_ERR_SHAPE, "clear_head_compact_rows: n_rows out of range");
+  compact_rows_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(labels, n_rows, row_index, count);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int rows_move(bool scatter, const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx,
+                     int32_t row_bytes, void* dst, int64_t dst_ld_bytes, void* stream) {
+  const char* who = scatter ? "clear_rows_scatter" : "clear_rows_gather";
+  if (!src || !dst || !row_index) return fail(CLEAR_ERR_NULL, "%s: null pointer", who);
+  if (n_idx < 0 || row_bytes <= 0 || (row_bytes & 3) || src_ld_bytes < row_bytes || dst_ld_bytes < row_bytes)
+    return fail(CLEAR_ERR_SHAPE, "%s: row_bytes must be a positive multiple of 4 within both strides", who);
+  const int align = (row_bytes & 15) ? 3 : 15;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)src_ld_bytes | (uintptr_t)dst_ld_bytes) & align))
+    return fail(CLEAR_ERR_ALIGN, "%s: pointers and strides must be %d-byte aligned", who, align + 1);
+  if (n_idx == 0) return 0;
+  const int lanes_per_row = (row_bytes & 15) ? ((row_bytes + 3) >> 2) : (row_bytes >> 4);
+  int64_t blocks = (n_idx * lanes_per_row + 255) / 256;
+  const int64_t cap = (int64_t)(device_sm_count() > 0 ? device_sm_count() : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  if (scatter)
+    rows_move_kernel<true><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(src), src_ld_bytes, row_index, n_idx, row_bytes, static_cast<uint8_t*>(dst), dst_ld_bytes);
+  else
+    rows_move_kernel<false><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(src), src_ld_bytes, row_index, n_idx, row_bytes, static_cast<uint8_t*>(dst), dst_ld_bytes);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_rows_gather(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx, int32_t row_bytes,
+                      void* dst, int64_t dst_ld_bytes, void* stream) {
+  return rows_move(false, src, src_ld_bytes, row_index, n_idx, row_bytes, dst, dst_ld_bytes, stream);
+}
+
+int clear_rows_scatter(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx, int32_t row_bytes,
+                       void* dst, int64_t dst_ld_bytes, void* stream) {
+  return rows_move(true, src, src_ld_bytes, row_index, n_idx, row_bytes, dst, dst_ld_bytes, stream);
 }
 
 int clear_head_count_valid(const int64_t* labels, int64_t n_rows, float* inv_count, void* stream) {

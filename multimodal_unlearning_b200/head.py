@@ -189,6 +189,41 @@ def reduce_sequences(loss_rows: torch.Tensor, n_seqs: int, seq_sums: torch.Tenso
                "clear_head_reduce_sequences")
 
 
+def compact_rows(labels: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """(row_index int32 [N], count int32 [1]) on the device: ascending indices of the rows with a label != -100."""
+    n = labels.numel()
+    idx = torch.empty(n, dtype=torch.int32, device=labels.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=labels.device)
+    _lib.check(_lib.load().clear_head_compact_rows(labels.data_ptr(), n, idx.data_ptr(), cnt.data_ptr(), _stream()),
+               "clear_head_compact_rows")
+    return idx, cnt
+
+
+def _rows_move(fn_name: str, src: torch.Tensor, idx: torch.Tensor, n_idx: int, dst: torch.Tensor) -> None:
+    """src / dst: 1-D or 2-D row-major tensors of one dtype; moves n_idx whole rows."""
+    esz = src.element_size()
+    width = src.shape[1] if src.dim() == 2 else 1
+    s_ld = (src.stride(0) if src.dim() == 2 else 1) * esz
+    d_ld = (dst.stride(0) if dst.dim() == 2 else 1) * esz
+    fn = getattr(_lib.load(), fn_name)
+    _lib.check(fn(src.data_ptr(), s_ld, idx.data_ptr(), n_idx, width * esz, dst.data_ptr(), d_ld, _stream()), fn_name)
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, n_idx: int) -> torch.Tensor:
+    dst = torch.empty((n_idx,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if n_idx:
+        _rows_move("clear_rows_gather", src, idx, n_idx, dst)
+    return dst
+
+
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, n_idx: int, n_rows: int) -> torch.Tensor:
+    """zeros [n_rows, ...] with row idx[i] = src[i]."""
+    dst = torch.zeros((n_rows,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if n_idx:
+        _rows_move("clear_rows_scatter", src, idx, n_idx, dst)
+    return dst
+
+
 # --------------------------------------------------------------------------------------------------
 # the fused forward+backward of one head invocation
 # --------------------------------------------------------------------------------------------------
@@ -234,7 +269,8 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
                       reduction: str = "reference", n_seqs: int | None = None,
                       row_weight: torch.Tensor | None = None, need_dhidden: bool = True, need_dweight: bool = True,
                       dweight_accum: torch.Tensor | None = None, block_rows: int | None = None,
-                      cta_group: int = 0, overlap: bool = False, dweight_target=None) -> HeadResult:
+                      cta_group: int = 0, overlap: bool = False, dweight_target=None,
+                      compact_ignored: bool = False) -> HeadResult:
     """One head invocation: loss = coef * norm * sum_i term_i, plus d loss/d hidden and d loss/d weight.
 
     hidden [N, H] bf16, weight [V, H] bf16; labels [N] int64 ALREADY SHIFTED (see shift_labels) for CE;
@@ -246,6 +282,10 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     dweight_target: a `distributed.FusedGradReducer.begin()` target — dW is not returned; every tile of it is
     reduce-added into the owner rank's buffer by the contraction itself (HeadResult.dweight is None; the reduced,
     averaged gradient comes from `reducer.finish(target)`).
+    compact_ignored (CE only): run the head on the rows whose label is not -100 only.  Ignored rows contribute nothing to
+    the loss, to dW or to their own dH (their dH rows are returned as zeros), so loss and gradients are those of the full
+    evaluation; in CLEAR's batches (padding + 576 image positions + question ignored) this removes most of the work.  Costs
+    one host read of the valid-row count (a synchronisation) — the trainers enable it, a bare call does not.
     overlap: issue the contractions and the row passes on two streams (see the staging comment below).  Off
     by default: under the 1 kW power cap the step is energy-bound and the overlap measured no gain on B200.
     """
@@ -284,6 +324,33 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         row_weight = row_weight.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         if row_weight.numel() != n:
             raise RuntimeError("row_weight must have one entry per row")
+
+    if compact_ignored and kind == KIND_CE:
+        idx, cnt = compact_rows(labels)
+        n_valid = int(cnt.item())                     # the one host synchronisation of this mode
+        if 0 < n_valid < n:
+            sub_reduction, sub_coef = reduction, coef
+            if reduction == "seq_mean":               # per-sequence sums are rebuilt from the scattered row terms below
+                if not n_seqs or n % n_seqs:
+                    raise RuntimeError("reduction='seq_mean' needs n_seqs dividing the number of rows")
+                sub_reduction, sub_coef = "sum", coef / n_seqs
+            sub = head_loss_fwd_bwd(gather_rows(hidden, idx, n_valid), weight, kind, labels=gather_rows(labels, idx, n_valid),
+                                    beta=beta, coef=sub_coef, reduction=sub_reduction,
+                                    row_weight=gather_rows(row_weight, idx, n_valid) if row_weight is not None else None,
+                                    need_dhidden=need_dhidden, need_dweight=need_dweight, dweight_accum=dweight_accum,
+                                    block_rows=block_rows, cta_group=cta_group, overlap=overlap, dweight_target=dweight_target)
+            loss_rows = scatter_rows(sub.loss_rows, idx, n_valid, n)
+            seq_loss = None
+            launches = sub.launches + 3 + (1 if row_weight is not None else 0) + 1
+            if n_seqs:
+                seq_loss = torch.empty(n_seqs, dtype=torch.float32, device=dev)
+                reduce_sequences(loss_rows, n_seqs, seq_loss)
+                launches += 1
+            dh = None
+            if need_dhidden:
+                dh = scatter_rows(sub.dhidden, idx, n_valid, n)
+                launches += 1
+            return HeadResult(sub.loss, seq_loss, dh, sub.dweight, loss_rows, launches)
 
     write_grad = need_dhidden or need_dweight
     blk = min(n, block_rows or DEFAULT_BLOCK_ROWS)
@@ -459,7 +526,7 @@ class _FusedHeadLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, beta, coef, reduction, n_seqs,
-                row_weight, block_rows):
+                row_weight, block_rows, compact_ignored):
         shape = hidden.shape
         h2 = hidden.reshape(-1, shape[-1])
         cast = h2.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16
@@ -474,7 +541,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         res = head_loss_fwd_bwd(hb, wb, kind, labels=labels, ref_hidden=rh, ref_weight=rw, ref_logits=rl, beta=beta,
                                 coef=coef, reduction=reduction, n_seqs=n_seqs, row_weight=row_weight,
                                 need_dhidden=ctx.needs_input_grad[0], need_dweight=ctx.needs_input_grad[1],
-                                block_rows=block_rows, dweight_target=target)
+                                block_rows=block_rows, dweight_target=target, compact_ignored=compact_ignored)
         dh = res.dhidden.reshape(shape) if res.dhidden is not None else None
         dw = res.dweight
         if reducer is not None:
@@ -496,18 +563,18 @@ class _FusedHeadLoss(torch.autograd.Function):
         g = g.to(torch.float32)
         gh = (dh * g.to(dh.dtype)) if dh is not None else None
         gw = (dw * g.to(dw.dtype)) if dw is not None else None
-        return (gh, gw) + (None,) * 11
+        return (gh, gw) + (None,) * 12
 
 
 def fused_head_loss(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, labels: torch.Tensor | None = None,
                     ref_hidden: torch.Tensor | None = None, ref_weight: torch.Tensor | None = None,
                     ref_logits: torch.Tensor | None = None, beta: float = 1.0, coef: float = 1.0,
                     reduction: str = "reference", n_seqs: int | None = None, row_weight: torch.Tensor | None = None,
-                    block_rows: int | None = None):
+                    block_rows: int | None = None, compact_ignored: bool = False):
     """Differentiable loss of one head invocation.  hidden [..., H]; labels already shifted, flat.
     Returns a 0-dim fp32 tensor (and the per-sequence sums when n_seqs is given)."""
     return _FusedHeadLoss.apply(hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, float(beta),
-                                float(coef), reduction, n_seqs, row_weight, block_rows)
+                                float(coef), reduction, n_seqs, row_weight, block_rows, bool(compact_ignored))
 
 
 @torch.no_grad()
@@ -518,5 +585,5 @@ def sequence_nll(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tenso
     res = head_loss_fwd_bwd(hidden.reshape(b * t, h).to(torch.bfloat16).contiguous(),
                             weight.to(torch.bfloat16).contiguous(), KIND_CE, labels=shift_labels(labels),
                             reduction="seq_mean", n_seqs=b, need_dhidden=False, need_dweight=False,
-                            block_rows=block_rows)
+                            block_rows=block_rows, compact_ignored=True)
     return res.seq_loss

@@ -155,7 +155,7 @@ class _Recipes:
         """`model(**split).loss` — HF causal-LM CE, mean over non-ignored shifted labels (A2)."""
         h, w, labels = self.fwd(split)
         return head.fused_head_loss(h, w, KIND_CE, labels=head.shift_labels(labels), coef=coef,
-                                    block_rows=self.block_rows)
+                                    block_rows=self.block_rows, compact_ignored=True)
 
     def _with_teacher(self, split, kind, coef, beta=1.0):
         h, w, _ = self.fwd(split)
@@ -184,7 +184,7 @@ class _Recipes:
         """get_batch_loss: per-sequence sums -> (mean over B scaled by coef, [B] sums) (A6c)."""
         h, w, labels = self.fwd(split)
         return head.fused_head_loss(h, w, KIND_CE, labels=head.shift_labels(labels), coef=coef, reduction="seq_mean",
-                                    n_seqs=h.shape[0], row_weight=row_weight, block_rows=self.block_rows)
+                                    n_seqs=h.shape[0], row_weight=row_weight, block_rows=self.block_rows, compact_ignored=True)
 
     def teacher_seq_logp(self, split, labels):
         rh, rw = self.tfwd(split)
@@ -226,7 +226,7 @@ class _Recipes:
         def weighted(h, w, labels, coef):
             return head.fused_head_loss(h, w, KIND_CE, labels=head.shift_labels(labels), coef=coef, reduction="seq_mean",
                                         n_seqs=h.shape[0], row_weight=wgt.repeat_interleave(h.shape[1]),
-                                        block_rows=self.block_rows)[0]
+                                        block_rows=self.block_rows, compact_ignored=True)[0]
 
         surrogate = weighted(hi, wi, li, 1.0) + weighted(hf, wf, lf, -1.0)  # gradient of the true loss
         return surrogate + (value - surrogate).detach()

@@ -526,3 +526,42 @@ def test_gemm_layouts_groups_and_tile_orders(cta_group, layout, raster):
     got = D[:, :n].float().cpu()
     assert (got - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
     assert (D[:, n:] == 7.0).all(), "columns beyond N must not be written"
+
+
+@pytest.mark.parametrize("reduction", ["reference", "seq_mean", "sum"])
+@pytest.mark.parametrize("valid_frac", [0.05, 0.5, 1.0, 0.0])
+def test_ce_row_compaction_is_exact(reduction, valid_frac):
+    """compact_ignored: the head evaluated on the non-ignored rows only gives the loss, dH (zeros on ignored rows) and dW
+    of the evaluation over every row — compared with the uncompacted kernels and, for the loss, with the oracle."""
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    b, t, h, v = 4, 96, 128, 1000
+    n = b * t
+    hid, w, _, _, y = _inputs(n, h, v, 91, dev)
+    g = torch.Generator().manual_seed(5)
+    keep = torch.rand(n, generator=g) < valid_frac
+    y = torch.where(keep, y, torch.full_like(y, -100))
+    rw = torch.rand(n, generator=g) if reduction == "seq_mean" else None
+    kw = dict(labels=y.to(dev), coef=-0.7, reduction=reduction, n_seqs=b if reduction == "seq_mean" else None,
+              row_weight=rw.to(dev) if rw is not None else None)
+    full = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, **kw)
+    comp = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, compact_ignored=True, **kw)
+    torch.cuda.synchronize()
+    if valid_frac == 0.0 and reduction == "reference":
+        assert torch.isnan(comp.loss).all() and torch.isnan(full.loss).all()      # mean over no rows, as HF
+        return
+    assert abs(comp.loss.item() - full.loss.item()) <= 1e-5 * max(abs(full.loss.item()), 1e-6)
+    assert torch.allclose(comp.loss_rows, full.loss_rows, rtol=1e-6, atol=0)
+    ignored = (~keep).to(dev)
+    assert (comp.dhidden[ignored] == 0).all() and (full.dhidden[ignored] == 0).all()
+    assert torch.equal(comp.dhidden, full.dhidden)        # row-wise results do not depend on which rows share a launch
+    if keep.any():
+        rel = ((comp.dweight.float() - full.dweight.float()).norm() / full.dweight.float().norm()).item()
+        assert rel <= 1e-2, rel                             # same products, different K blocking of the bf16 inputs
+    if reduction == "seq_mean":
+        assert torch.allclose(comp.seq_loss, full.seq_loss, rtol=1e-5, atol=1e-6)
+    # forward only
+    f_only = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), HO.KIND_CE, compact_ignored=True, need_dhidden=False,
+                                    need_dweight=False, **kw)
+    assert f_only.dhidden is None and f_only.dweight is None
+    assert abs(f_only.loss.item() - full.loss.item()) <= 1e-5 * max(abs(full.loss.item()), 1e-6)
