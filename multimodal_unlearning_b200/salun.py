@@ -143,6 +143,51 @@ class SaliencyState:
             yield th, {n: self.layout.view(flat, i) for i, n in enumerate(self.layout.names)}
 
 
+def sharded_masks(state: SaliencyState, thresholds: Sequence[float] = REFERENCE_THRESHOLDS, group=None,
+                  reduce_acc: bool = True) -> list[torch.Tensor]:
+    """Data-parallel mask generation.  The reference sums SIGNED gradients over all forget batches
+    before taking |.| (generate_mask.py:44 then :49), so with the batches dealt out to ranks the accumulators are
+    all-reduced (sum, bf16) first.  Its thresholds are per tensor (:54-85): tensors are independent units — rank r
+    computes the masks of the tensors `distributed.partition_units` deals to it (no collective on that path) and the
+    bit-packed results are exchanged.  Returns one flat bit-packed mask per threshold in `state.layout`, identical on
+    every rank (feed `layout`-offset slices to MaskedAdamW, or `unpack_mask` them)."""
+    import torch.distributed as dist
+
+    from . import distributed as D
+
+    lay = state.layout
+    world = D.world_size()
+    if world == 1:
+        sel = state.select(thresholds)
+        return [state.mask_flat(sel, j, packed=True) for j in range(len(thresholds))]
+    rank = dist.get_rank(group)
+    if reduce_acc:
+        dist.all_reduce(state.acc, op=dist.ReduceOp.SUM, group=group)
+    units = D.partition_units(lay.numels, world)
+    sub_layouts = [FlatLayout([(lay.names[i], lay.shapes[i]) for i in units[r]]) for r in range(world)]
+    mine = sub_layouts[rank]
+    sub = SaliencyState(mine, state.device)
+    for j, i in enumerate(units[rank]):
+        n = lay.numels[i]
+        sub.acc[mine.offsets[j]: mine.offsets[j] + n].copy_(state.acc[lay.offsets[i]: lay.offsets[i] + n])
+    sel = sub.select(thresholds) if units[rank] else None
+    out = []
+    for t in range(len(thresholds)):
+        full = torch.zeros(lay.total // 8, dtype=torch.uint8, device=state.device)
+        for r in range(world):
+            lr = sub_layouts[r]
+            if lr.total == 0:
+                continue
+            buf = sub.mask_flat(sel, t, packed=True) if r == rank else torch.empty(lr.total // 8, dtype=torch.uint8, device=state.device)
+            dist.broadcast(buf, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+            for j, i in enumerate(units[r]):
+                nb = (lay.numels[i] + 7) // 8
+                full[lay.offsets[i] // 8: lay.offsets[i] // 8 + nb].copy_(buf[lr.offsets[j] // 8: lr.offsets[j] // 8 + nb])
+        out.append(full)
+    state.launches += 3 * len(thresholds) + 2
+    return out
+
+
 def pack_mask(mask: torch.Tensor) -> torch.Tensor:
     """int8 / bool mask (any shape, CUDA) -> bit-packed uint8 [ceil(numel / 8)] (bit i & 7 of byte i >> 3)."""
     if not mask.is_cuda:

@@ -136,3 +136,51 @@ def test_trainer_under_ddp_with_fused_head_allreduce(tmp_path):
     s.close()
     mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ddp_ok0").exists() and (tmp_path / "ddp_ok1").exists()
+
+
+def _salun_worker(rank, world, port, out_dir):
+    """Forget batches dealt out to two ranks: all-reduced signed accumulators, tensors dealt out to ranks for the
+    per-tensor thresholds, bit-packed masks exchanged — equal to the single-process oracle masks, bit for bit."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import numpy as np
+    import torch.distributed as dist
+    from multimodal_unlearning_b200 import distributed as D
+    from multimodal_unlearning_b200 import salun
+    from oracle import salun_oracle as SO
+    D.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    shapes = [("a", (300, 70)), ("b", (1001,)), ("c", (64, 64)), ("d", (5,)), ("e", (2048, 33))]
+    layout = salun.FlatLayout(shapes)
+    state = salun.SaliencyState(layout, dev)
+    grads = []
+    for r in range(world):   # every rank can rebuild every rank's gradients (for the oracle)
+        g = torch.Generator().manual_seed(50 + r)
+        grads.append({n: ((torch.randn(*s, generator=g) * 4).round() / 4).to(torch.bfloat16) for n, s in shapes})
+    flat = torch.zeros(layout.total, dtype=torch.bfloat16)
+    for i, (n, _) in enumerate(shapes):
+        flat[layout.offsets[i]: layout.offsets[i] + layout.numels[i]] = grads[rank][n].reshape(-1)
+    state.accumulate_flat(flat.to(dev))
+    ths = (0.1, 0.5, 1.0)
+    packed = salun.sharded_masks(state, ths)
+    total = {n: SO.accumulate(grads[0][n], grads[1][n]) for n, _ in shapes}
+    want = SO.masks(total, ths)
+    for t, th in enumerate(ths):
+        for i, (n, s) in enumerate(shapes):
+            nb = (layout.numels[i] + 7) // 8
+            got = salun.unpack_mask(packed[t][layout.offsets[i] // 8: layout.offsets[i] // 8 + nb].clone(), s)
+            assert np.array_equal(got.cpu().numpy(), want[th][n]), (th, n)
+    (Path(out_dir) / f"salun_ok{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_salun_masks(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_salun_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "salun_ok0").exists() and (tmp_path / "salun_ok1").exists()
