@@ -104,3 +104,21 @@ def test_dweight_slabs_partition_the_vocabulary():
                 prev = r1.value
             assert prev == vocab
     assert lib.clear_head_dweight_slab(100, 9, 0, 0, C.byref(C.c_int32()), C.byref(C.c_int32())) < 0
+
+
+def test_plain_c_consumer_links_and_runs(tmp_path):
+    """tests/c/abi_consumer.c: the header compiles as C11 (-Wall -Wextra -Werror), the library links without Python or torch,
+    and argument errors come back as negative ClearStatus codes before any launch."""
+    import shutil
+    import subprocess
+    from multimodal_unlearning_b200 import build as B
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    lib = B.build()
+    exe = tmp_path / "abi_consumer"
+    cmd = [gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "c" / "abi_consumer.c"),
+           "-o", str(exe), f"-L{lib.parent}", f"-l:{lib.name}", f"-Wl,-rpath,{lib.parent}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.strip().endswith("ok"), run.stdout + run.stderr
