@@ -199,6 +199,53 @@ int clear_dweight_allgather(const void* local_buf, void* multicast_buf, void* co
                             int32_t row0, int32_t row1, int32_t hidden_dim, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Loss head in ONE call: everything the reference evaluates between "the trunk produced hidden states"
+ * and "autograd filled dH and lm_head.weight.grad" for one `model(**split)` — MMTrainerForgetting.compute_loss
+ * mm/trainer.py:168-449, CustomTrainerForgetting.compute_loss nlp/dataloader.py:144-459.  Rows are streamed in blocks of
+ * block_rows through the three stages above; the workspace holds the one bf16 staging block per projected operand.
+ *   loss      = coef * norm * sum_i loss_rows[i]   with the reference's normalisation (reduction = REFERENCE: CE mean over
+ *               non-ignored rows, KL / N, mm NPO (2/beta) mean over N V, entropy raw sum), a plain sum, or the mean
+ *               over n_seqs of per-sequence sums (get_batch_loss, mm/trainer_utils.py:73-81);
+ *   dhidden   = d loss / d hidden (bf16), dweight = d loss / d weight (bf16 or fp32; dweight_accumulate: +=), or the
+ *               fused reduce-scatter targets dweight_peers (see ClearBackwardArgs); all NULL = forward only.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum ClearReduction {
+  CLEAR_REDUCE_REFERENCE = 0,
+  CLEAR_REDUCE_SUM = 1,
+  CLEAR_REDUCE_SEQ_MEAN = 2,
+} ClearReduction;
+
+typedef struct ClearHeadArgs {
+  const void* hidden;      /* bf16 [n_rows, hidden_ld] */
+  const void* weight;      /* bf16 [vocab, weight_ld] */
+  const int64_t* labels;   /* CE: shifted labels [n_rows], -100 = ignored; NULL for the other kinds */
+  const void* ref_hidden;  /* frozen teacher as (hidden, weight): projected here block by block ... */
+  const void* ref_weight;
+  const void* ref_logits;  /* ... or as materialised bf16 logits [n_rows, ref_logits_ld] */
+  const float* row_weight; /* optional [n_rows] */
+  float* loss;             /* out fp32 [1] */
+  float* loss_rows;        /* out fp32 [n_rows]: unscaled row terms */
+  float* seq_loss;         /* out fp32 [n_seqs] per-sequence sums of the row terms, or NULL */
+  void* dhidden;           /* out bf16 [n_rows, dhidden_ld], or NULL */
+  void* dweight;           /* out bf16 / fp32 [vocab, dweight_ld], or NULL */
+  void* dweight_peers[8];  /* fused gradient reduce-scatter: see ClearBackwardArgs */
+  int32_t n_peers;
+  int64_t hidden_ld, weight_ld, ref_hidden_ld, ref_weight_ld, ref_logits_ld, dhidden_ld, dweight_ld;
+  int64_t n_rows;
+  int32_t hidden_dim, vocab;
+  int32_t kind;            /* ClearLossKind */
+  float beta;              /* NPO exponent (loss_beta) */
+  float coef;              /* the recipe's coefficient on this term (e.g. -loss_beta for a forget term) */
+  int32_t reduction;       /* ClearReduction */
+  int32_t n_seqs;
+  int32_t block_rows;      /* rows staged per pass; 0 = 8192 */
+  int32_t dweight_f32, dweight_accumulate;
+  int32_t cta_group;
+} ClearHeadArgs;
+int clear_head_loss_workspace_bytes(const ClearHeadArgs* args, size_t* out_bytes);
+int clear_head_loss_fwd_bwd(const ClearHeadArgs* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SalUn saliency mask (methods/salun/generate_mask.py:17-89) and the masked update.
  * All tensors of a model live in flat buffers; `seg_offsets` (host, n_segs+1 int64, element units,
  * every offset a multiple of 8) delimits the per-parameter tensors — thresholds are per tensor, as

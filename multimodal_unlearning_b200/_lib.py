@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = (
     "clear_masked_adamw", "clear_reduce_partials_elems", "clear_grad_sqnorm", "clear_clip_coef", "clear_param_l1l0",
     "clear_param_l1_grad", "clear_grad_scale", "clear_saliency_mask_bits", "clear_mask_pack", "clear_mask_unpack",
     "clear_head_dweight_slab", "clear_dweight_allgather", "clear_head_compact_rows", "clear_rows_gather", "clear_rows_scatter",
+    "clear_head_loss_workspace_bytes", "clear_head_loss_fwd_bwd",
 )
 
 
@@ -57,6 +58,21 @@ class BackwardArgs(C.Structure):
                 ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("dweight_f32", C.c_int32),
                 ("accumulate", C.c_int32), ("cta_group", C.c_int32), ("dhidden_ws", C.c_void_p),
                 ("dweight_peers", C.c_void_p * 8), ("n_peers", C.c_int32)]
+
+
+REDUCE_REFERENCE, REDUCE_SUM, REDUCE_SEQ_MEAN = 0, 1, 2
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [("hidden", C.c_void_p), ("weight", C.c_void_p), ("labels", C.c_void_p), ("ref_hidden", C.c_void_p),
+                ("ref_weight", C.c_void_p), ("ref_logits", C.c_void_p), ("row_weight", C.c_void_p), ("loss", C.c_void_p),
+                ("loss_rows", C.c_void_p), ("seq_loss", C.c_void_p), ("dhidden", C.c_void_p), ("dweight", C.c_void_p),
+                ("dweight_peers", C.c_void_p * 8), ("n_peers", C.c_int32),
+                ("hidden_ld", C.c_int64), ("weight_ld", C.c_int64), ("ref_hidden_ld", C.c_int64), ("ref_weight_ld", C.c_int64),
+                ("ref_logits_ld", C.c_int64), ("dhidden_ld", C.c_int64), ("dweight_ld", C.c_int64), ("n_rows", C.c_int64),
+                ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("kind", C.c_int32), ("beta", C.c_float), ("coef", C.c_float),
+                ("reduction", C.c_int32), ("n_seqs", C.c_int32), ("block_rows", C.c_int32), ("dweight_f32", C.c_int32),
+                ("dweight_accumulate", C.c_int32), ("cta_group", C.c_int32)]
 
 
 class AdamWArgs(C.Structure):
@@ -117,6 +133,8 @@ def load() -> C.CDLL:
     lib.clear_head_compact_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.clear_rows_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     lib.clear_rows_scatter.argtypes = lib.clear_rows_gather.argtypes
+    lib.clear_head_loss_workspace_bytes.argtypes = [C.POINTER(HeadArgs), C.POINTER(C.c_size_t)]
+    lib.clear_head_loss_fwd_bwd.argtypes = [C.POINTER(HeadArgs), C.c_void_p, C.c_size_t, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError here = the .so is stale / does not match include/clear_b200.h
     if lib.clear_abi_version() != 1:

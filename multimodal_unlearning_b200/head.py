@@ -360,22 +360,23 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     launches = 0
 
     host_scale, grad_scale, per_valid = _normalisation(kind, reduction, n, v, beta, n_seqs)
+    pipelined = overlap and n_blocks >= 2 and StageTimer.active is None
+    one_call = not pipelined and StageTimer.active is None
     inv_count = None
-    if per_valid:
+    if per_valid and not one_call:
         inv_count = torch.empty(1, dtype=torch.float32, device=dev)
         count_valid(labels, inv_count)
-        launches += 1
+    launches += int(per_valid)
 
     # Staging: two student blocks (block b+1 is projected while block b is still being consumed) and one
     # teacher block.  The row pass is bound by the XU pipe and HBM, the contractions by the tensor pipe, so
     # they are issued on two streams and overlap: row pass of block b runs beside the student projection of
     # block b+1 and beside the backward contractions of block b-1.
-    pipelined = overlap and n_blocks >= 2 and StageTimer.active is None
-    n_stage = 2 if pipelined else 1
+    n_stage = 2 if pipelined else (0 if one_call else 1)   # the one-call entry point carves its staging from a workspace
     zs = [torch.empty((blk, ld), dtype=torch.bfloat16, device=dev) for _ in range(n_stage)]
     parts = [torch.empty((blk, nt, 2), dtype=torch.float32, device=dev) for _ in range(n_stage)]
     zr = rpart = None
-    if needs_ref:
+    if needs_ref and not one_call:
         rpart = torch.empty((blk, nt, 2), dtype=torch.float32, device=dev)
         if ref_logits is None:
             zr = torch.empty((blk, ld), dtype=torch.bfloat16, device=dev)
@@ -400,6 +401,43 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
             dweight = torch.empty_like(weight)
         else:
             dweight = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+
+    launches += n_blocks * (2 + int(needs_ref) + (int(need_dhidden) + int(need_dweight) if write_grad else 0)) + 1 + int(bool(n_seqs))
+    if one_call:
+        # The whole invocation in ONE C call (clear_head_loss_fwd_bwd): the block loop, the normalisations and the
+        # workspace carving run in the library; this function only owns the tensors.
+        if n_seqs and n % n_seqs:
+            raise RuntimeError("n_seqs must divide the number of rows")
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        seq_loss = torch.empty(n_seqs, dtype=torch.float32, device=dev) if n_seqs else None
+        red = {"reference": _lib.REDUCE_REFERENCE, "sum": _lib.REDUCE_SUM, "seq_mean": _lib.REDUCE_SEQ_MEAN}[reduction]
+        a = _lib.HeadArgs(hidden=hidden.data_ptr(), weight=weight.data_ptr(), labels=_ptr(labels) if kind == KIND_CE else None,
+                          ref_hidden=_ptr(ref_hidden) if (needs_ref and ref_logits is None) else None,
+                          ref_weight=_ptr(ref_weight) if (needs_ref and ref_logits is None) else None,
+                          ref_logits=_ptr(ref_logits) if needs_ref else None, row_weight=_ptr(row_weight),
+                          loss=loss.data_ptr(), loss_rows=loss_rows.data_ptr(), seq_loss=_ptr(seq_loss), dhidden=_ptr(dhidden),
+                          dweight=_ptr(dweight), n_peers=len(peers) if peers else 0, hidden_ld=hidden.stride(0),
+                          weight_ld=weight.stride(0),
+                          ref_hidden_ld=ref_hidden.stride(0) if (needs_ref and ref_logits is None) else 0,
+                          ref_weight_ld=ref_weight.stride(0) if (needs_ref and ref_logits is None) else 0,
+                          ref_logits_ld=ref_logits.stride(0) if (needs_ref and ref_logits is not None) else 0,
+                          dhidden_ld=dhidden.stride(0) if dhidden is not None else 0,
+                          dweight_ld=dweight.stride(0) if dweight is not None else h, n_rows=n, hidden_dim=h, vocab=v, kind=kind,
+                          beta=beta, coef=coef, reduction=red, n_seqs=n_seqs or 0, block_rows=blk,
+                          dweight_f32=int(dweight is not None and dweight.dtype == torch.float32),
+                          dweight_accumulate=int(dweight_accum is not None), cta_group=cta_group)
+        if peers:
+            for r, ptr in enumerate(peers):
+                a.dweight_peers[r] = ptr
+        need = C.c_size_t()
+        _lib.check(lib.clear_head_loss_workspace_bytes(C.byref(a), C.byref(need)), "clear_head_loss_workspace_bytes")
+        ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
+        if peers:
+            torch.cuda.current_stream().wait_event(dweight_target.ready)   # owners zeroed their slabs, all ranks agreed
+        _lib.check(lib.clear_head_loss_fwd_bwd(C.byref(a), ws.data_ptr(), need.value, _stream()), "clear_head_loss_fwd_bwd")
+        if need_dweight and peers is None and dweight_accum is None and dweight.dtype != torch.bfloat16:
+            dweight = dweight.to(torch.bfloat16)
+        return HeadResult(loss, seq_loss, dhidden, dweight if peers is None else None, loss_rows, launches)
 
     # fp32 scratch for a split-K dH contraction (used only when the library finds the plain one wave-starved)
     dh_ws = torch.empty((blk, h), dtype=torch.float32, device=dev) if need_dhidden and h % 8 == 0 else None
@@ -438,7 +476,6 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
                  dweight if (need_dweight and peers is None) else None, accumulate=(dweight_accum is not None) or b > 0,
                  cta_group=cta_group, dhidden_ws=dh_ws, dweight_peers=peers)
 
-    launches += n_blocks * (2 + int(needs_ref) + (int(need_dhidden) + int(need_dweight) if write_grad else 0))
     if not pipelined:
         for b in range(n_blocks):
             do_project(b)
@@ -474,14 +511,12 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
 
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     reduce_rows(loss_rows, loss, coef * host_scale, inv_count)
-    launches += 1
     seq_loss = None
     if n_seqs:
         if n % n_seqs:
             raise RuntimeError("n_seqs must divide the number of rows")
         seq_loss = torch.empty(n_seqs, dtype=torch.float32, device=dev)
         reduce_sequences(loss_rows, n_seqs, seq_loss)
-        launches += 1
     if need_dweight and peers is None and dweight_accum is None and dweight.dtype != torch.bfloat16:
         dweight = dweight.to(torch.bfloat16)
     del lib

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header_field_order():
     from multimodal_unlearning_b200 import _lib
     for cname, cls in (("ClearGemmArgs", _lib.GemmArgs), ("ClearProjectArgs", _lib.ProjectArgs),
                        ("ClearRowLossArgs", _lib.RowLossArgs), ("ClearBackwardArgs", _lib.BackwardArgs),
-                       ("ClearAdamWArgs", _lib.AdamWArgs)):
+                       ("ClearAdamWArgs", _lib.AdamWArgs), ("ClearHeadArgs", _lib.HeadArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), HEADER, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
