@@ -542,6 +542,38 @@ def _ref_lse(ref_logits: torch.Tensor, lse_part: torch.Tensor, vocab: int) -> No
 
 
 # --------------------------------------------------------------------------------------------------
+# torch.library operator: the PyTorch-visible form of clear_head_loss_fwd_bwd (SURVEY.md §8b "inner operator boundary")
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("clear_b200::head_loss", mutates_args=())
+def head_loss_op(hidden: torch.Tensor, weight: torch.Tensor, kind: int, labels: torch.Tensor | None,
+                 ref_hidden: torch.Tensor | None, ref_weight: torch.Tensor | None, ref_logits: torch.Tensor | None,
+                 row_weight: torch.Tensor | None, beta: float, coef: float, reduction: str, n_seqs: int, block_rows: int,
+                 need_dhidden: bool, need_dweight: bool,
+                 compact_ignored: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(loss [1] fp32, seq_loss [n_seqs] fp32, dhidden [N, H] bf16, dweight [V, H] bf16, loss_rows [N] fp32) of one
+    head invocation; outputs that were not requested come back as empty tensors.  hidden [N, H], weight [V, H] bf16 CUDA;
+    labels shifted, flat.  n_seqs = 0 / block_rows = 0 mean "none" / "default"."""
+    res = head_loss_fwd_bwd(hidden, weight, kind, labels=labels, ref_hidden=ref_hidden, ref_weight=ref_weight,
+                            ref_logits=ref_logits, beta=beta, coef=coef, reduction=reduction, n_seqs=n_seqs or None,
+                            row_weight=row_weight, need_dhidden=need_dhidden, need_dweight=need_dweight,
+                            block_rows=block_rows or None, compact_ignored=compact_ignored)
+    none = lambda dt: torch.empty(0, dtype=dt, device=hidden.device)
+    return (res.loss, res.seq_loss if res.seq_loss is not None else none(torch.float32),
+            res.dhidden if res.dhidden is not None else none(torch.bfloat16),
+            res.dweight if res.dweight is not None else none(torch.bfloat16), res.loss_rows)
+
+
+@head_loss_op.register_fake
+def _(hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, row_weight, beta, coef, reduction, n_seqs, block_rows,
+      need_dhidden, need_dweight, compact_ignored):
+    f32 = dict(dtype=torch.float32, device=hidden.device)
+    return (torch.empty(1, **f32), torch.empty(n_seqs, **f32),
+            torch.empty_like(hidden) if need_dhidden else torch.empty(0, dtype=torch.bfloat16, device=hidden.device),
+            torch.empty_like(weight) if need_dweight else torch.empty(0, dtype=torch.bfloat16, device=hidden.device),
+            torch.empty(hidden.shape[0], **f32))
+
+
+# --------------------------------------------------------------------------------------------------
 # autograd boundary
 # --------------------------------------------------------------------------------------------------
 _DW_REDUCER = None
@@ -572,11 +604,20 @@ class _FusedHeadLoss(torch.autograd.Function):
         rl = ref_logits.reshape(-1, ref_logits.shape[-1]).to(torch.bfloat16).contiguous() if ref_logits is not None else None
         reducer = _DW_REDUCER if (ctx.needs_input_grad[1] and _DW_REDUCER is not None
                                   and tuple(_DW_REDUCER.shape) == tuple(wb.shape)) else None
-        target = reducer.begin() if reducer is not None else None
-        res = head_loss_fwd_bwd(hb, wb, kind, labels=labels, ref_hidden=rh, ref_weight=rw, ref_logits=rl, beta=beta,
-                                coef=coef, reduction=reduction, n_seqs=n_seqs, row_weight=row_weight,
-                                need_dhidden=ctx.needs_input_grad[0], need_dweight=ctx.needs_input_grad[1],
-                                block_rows=block_rows, dweight_target=target, compact_ignored=compact_ignored)
+        if reducer is None:
+            # through the registered operator (torch.ops.clear_b200.head_loss)
+            loss, seq_loss, dh, dw, _rows = torch.ops.clear_b200.head_loss(
+                hb, wb, kind, labels, rh, rw, rl, row_weight, beta, coef, reduction, n_seqs or 0, block_rows or 0,
+                ctx.needs_input_grad[0], ctx.needs_input_grad[1], compact_ignored)
+            res = HeadResult(loss, seq_loss if n_seqs else None, dh if dh.numel() else None, dw if dw.numel() else None, _rows, 0)
+        else:
+            # the fused data-parallel reducer hands the contraction a set of peer buffers: a Python object, outside the
+            # operator schema
+            target = reducer.begin()
+            res = head_loss_fwd_bwd(hb, wb, kind, labels=labels, ref_hidden=rh, ref_weight=rw, ref_logits=rl, beta=beta,
+                                    coef=coef, reduction=reduction, n_seqs=n_seqs, row_weight=row_weight,
+                                    need_dhidden=ctx.needs_input_grad[0], need_dweight=ctx.needs_input_grad[1],
+                                    block_rows=block_rows, dweight_target=target, compact_ignored=compact_ignored)
         dh = res.dhidden.reshape(shape) if res.dhidden is not None else None
         dw = res.dweight
         if reducer is not None:

@@ -167,3 +167,21 @@ def test_teacher_cache_lru_eviction_and_keys():
     img2 = {**img, "pixel_values": torch.ones(1, 3, 2, 2)}
     k1 = TeacherCache.sample_keys(img2, image_token_id=9)
     assert k0[0] != k1[0] and k0[1] == k1[1]            # only the sample that owns the image changes
+
+
+def test_head_loss_operator_is_registered_with_a_fake_kernel():
+    """torch.ops.clear_b200.head_loss: the PyTorch custom-op layer over the C ABI.  Shape / dtype propagation runs without
+    a GPU (fake tensors); the real kernel refuses CPU tensors (no fallback)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from multimodal_unlearning_b200 import head  # noqa: F401  (registers the operator)
+    op = torch.ops.clear_b200.head_loss
+    with FakeTensorMode():
+        h = torch.empty(64, 128, dtype=torch.bfloat16, device="cuda")
+        w = torch.empty(1000, 128, dtype=torch.bfloat16, device="cuda")
+        y = torch.empty(64, dtype=torch.int64, device="cuda")
+        loss, seq, dh, dw, rows = op(h, w, 0, y, None, None, None, None, 1.0, 1.0, "seq_mean", 4, 0, True, False, True)
+        assert loss.shape == (1,) and seq.shape == (4,) and dh.shape == (64, 128) and dw.numel() == 0 and rows.shape == (64,)
+        assert dh.dtype == torch.bfloat16 and loss.dtype == torch.float32
+    with pytest.raises(RuntimeError, match="CUDA"):
+        op(torch.zeros(8, 16, dtype=torch.bfloat16), torch.zeros(32, 16, dtype=torch.bfloat16), 0, torch.zeros(8, dtype=torch.int64),
+           None, None, None, None, 1.0, 1.0, "reference", 0, 0, True, True, False)
