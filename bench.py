@@ -133,6 +133,24 @@ def cpu_reference_rate(sample_rows: int, reps: int):
     return sample_rows / best, torch.get_num_threads(), best
 
 
+def cpu_salun_rate(n_elems: int = 1 << 24):
+    """parameters/s of the reference's per-tensor, per-threshold mask (generate_mask.py:61-72: fp16 |grad| keys, descending
+    sort, top-k -> int8) on the host, restated by the oracle (stable sort), on a slice of n_elems synthetic gradients."""
+    import numpy as np
+    import torch
+    from oracle import salun_oracle as SO
+
+    g = torch.Generator().manual_seed(0)
+    acc = (1e-3 * torch.randn(n_elems, generator=g)).to(torch.bfloat16)
+    t0 = time.perf_counter()
+    keys = SO.saliency_keys(acc)
+    mask = SO.mask_of_keys(keys, 0.5)
+    dt = time.perf_counter() - t0
+    assert int(mask.sum()) == int(0.5 * n_elems)
+    return {"value": n_elems / dt, "unit": "parameters/s (one threshold)", "cores": 1, "kind": "port",
+            "sample": f"{n_elems} of 6.74e9 parameters, one tensor, threshold 0.5, numpy stable argsort ({dt:.2f} s)"}
+
+
 def run_reference_arm(args, rank: int):
     if rank != 0:
         return
@@ -343,6 +361,8 @@ def main():
             sys.path.insert(0, str(ROOT / "tools"))
             import bench_salun
             salun_res = bench_salun.run(layers=args.salun_layers, reps=3, peak_gbs=_peaks()["hbm_gbs"])
+            if not args.no_cpu_baseline:
+                salun_res["cpu_baseline"] = cpu_salun_rate()
             salun_res["workload"] = ("SalUn over the Llama-2-7B parameter list (synthetic bf16 grads 1e-3*randn): accumulate, "
                                      "histogram+select for 10 thresholds, one int8 mask, one masked AdamW step; "
                                      "frac = algorithmic bytes / time / measured HBM copy peak")
