@@ -234,8 +234,8 @@ typedef struct ClearHeadArgs {
   int64_t n_rows;
   int32_t hidden_dim, vocab;
   int32_t kind;            /* ClearLossKind */
-  float beta;              /* NPO exponent (loss_beta) */
-  float coef;              /* the recipe's coefficient on this term (e.g. -loss_beta for a forget term) */
+  double beta;             /* NPO exponent (loss_beta); double: the scale factors are formed in double, rounded once */
+  double coef;             /* the recipe's coefficient on this term (e.g. -loss_beta for a forget term) */
   int32_t reduction;       /* ClearReduction */
   int32_t n_seqs;
   int32_t block_rows;      /* rows staged per pass; 0 = 8192 */

@@ -70,7 +70,7 @@ class HeadArgs(C.Structure):
                 ("dweight_peers", C.c_void_p * 8), ("n_peers", C.c_int32),
                 ("hidden_ld", C.c_int64), ("weight_ld", C.c_int64), ("ref_hidden_ld", C.c_int64), ("ref_weight_ld", C.c_int64),
                 ("ref_logits_ld", C.c_int64), ("dhidden_ld", C.c_int64), ("dweight_ld", C.c_int64), ("n_rows", C.c_int64),
-                ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("kind", C.c_int32), ("beta", C.c_float), ("coef", C.c_float),
+                ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("kind", C.c_int32), ("beta", C.c_double), ("coef", C.c_double),
                 ("reduction", C.c_int32), ("n_seqs", C.c_int32), ("block_rows", C.c_int32), ("dweight_f32", C.c_int32),
                 ("dweight_accumulate", C.c_int32), ("cta_group", C.c_int32)]
 

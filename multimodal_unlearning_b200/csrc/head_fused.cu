@@ -38,7 +38,7 @@ int make_plan(const ClearHeadArgs* a, Plan* p) {
   if (p->needs_ref && !a->ref_logits && (!a->ref_hidden || !a->ref_weight))
     return fail(CLEAR_ERR_NULL, "clear_head_loss: kind %d needs the frozen teacher: ref_hidden + ref_weight, or ref_logits", a->kind);
   if (a->kind == CLEAR_KIND_CE && !a->labels) return fail(CLEAR_ERR_NULL, "clear_head_loss: CE needs labels");
-  if (a->kind == CLEAR_KIND_NPO && !(a->beta > 0.f)) return fail(CLEAR_ERR_SHAPE, "clear_head_loss: NPO beta must be > 0");
+  if (a->kind == CLEAR_KIND_NPO && !(a->beta > 0.0)) return fail(CLEAR_ERR_SHAPE, "clear_head_loss: NPO beta must be > 0");
   if (a->n_peers < 0 || a->n_peers > 8) return fail(CLEAR_ERR_SHAPE, "clear_head_loss: 0 <= n_peers <= 8");
   if (a->n_peers > 0 && a->dweight) return fail(CLEAR_ERR_KIND, "clear_head_loss: pass dweight or dweight_peers, not both");
   p->write_grad = a->dhidden || a->dweight || a->n_peers > 0;
@@ -157,7 +157,7 @@ int clear_head_loss_fwd_bwd(const ClearHeadArgs* a, void* workspace, size_t ws_b
     ra.loss_rows = a->loss_rows + r0;
     ra.logits_ld = p.ld; ra.ref_ld = ref_ld;
     ra.n_rows = rows; ra.vocab = a->vocab; ra.kind = a->kind;
-    ra.grad_scale = p.grad_scale; ra.beta = a->beta; ra.write_grad = p.write_grad ? 1 : 0;
+    ra.grad_scale = p.grad_scale; ra.beta = (float)a->beta; ra.write_grad = p.write_grad ? 1 : 0;
     if ((rc = clear_head_rowloss(&ra, stream))) return rc;
 
     if (p.write_grad) {

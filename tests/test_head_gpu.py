@@ -565,3 +565,24 @@ def test_ce_row_compaction_is_exact(reduction, valid_frac):
                                     need_dweight=False, **kw)
     assert f_only.dhidden is None and f_only.dweight is None
     assert abs(f_only.loss.item() - full.loss.item()) <= 1e-5 * max(abs(full.loss.item()), 1e-6)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_one_call_entry_equals_the_staged_entry_points(kind):
+    """clear_head_loss_fwd_bwd (one C call, workspace carved in the library) and the same stages driven one by one from
+    Python (what bench.py instruments with per-launch events) are the same computation, bit for bit."""
+    from multimodal_unlearning_b200 import head
+    dev = torch.device("cuda:0")
+    n, h, v = 300, 128, 1000
+    hid, w, rh, rw, y = _inputs(n, h, v, 33 + kind, dev)
+    y[::5] = -100
+    kw = dict(labels=y.to(dev), ref_hidden=rh.to(dev), ref_weight=rw.to(dev), beta=0.7 if kind == HO.KIND_NPO else 1.0, coef=-0.7,
+              block_rows=128)
+    one = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), kind, **kw)
+    with head.StageTimer() as st:
+        staged = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), kind, **kw)
+    summ = st.summary()
+    assert any(k.startswith("gemm") for k in summ) and "rowloss" in summ
+    assert torch.equal(one.loss, staged.loss) and torch.equal(one.loss_rows, staged.loss_rows)
+    assert torch.equal(one.dhidden, staged.dhidden) and torch.equal(one.dweight, staged.dweight)
+    assert one.launches == staged.launches
