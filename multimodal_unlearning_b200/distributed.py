@@ -161,6 +161,8 @@ class FusedGradReducer:
         with torch.cuda.stream(self.stream):
             hdl.barrier(channel=0)                              # every rank's tiles have landed at their owners
             mc = int(hdl.multicast_ptr or 0)                    # 0: no NVSwitch multicast on this system -> peer stores
+            if os.environ.get("CLEAR_NO_MULTICAST") == "1":     # test hook for the peer-store path
+                mc = 0
             table = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
             _lib.check(self.lib.clear_dweight_allgather(buf.data_ptr(), mc or None, table, self.world, buf.stride(0), self.row0,
                                                         self.row1, self.shape[1], self.scale,

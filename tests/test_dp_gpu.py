@@ -41,7 +41,8 @@ def _worker(rank, world, port, out_dir):
     # the same mean, fused into the contraction: reduce-scatter in the dW epilogue over NVLink + multicast all-gather
     fused = D.FusedGradReducer((v, h), dev, average=True)
     nccl_dw = res.dweight.clone()
-    for it in range(3):                                        # three steps: both buffers and a buffer reuse
+    for it in range(4):                                        # both buffers, a buffer reuse, and (last) the peer-store all-gather
+        os.environ["CLEAR_NO_MULTICAST"] = "1" if it == 3 else "0"
         tgt = fused.begin()
         r2 = head.head_loss_fwd_bwd(hid[sl], wgt, KIND_KL_FWD, ref_hidden=ref[sl], ref_weight=wgt, dweight_target=tgt,
                                     block_rows=256 if it == 1 else None)   # it == 1: two row blocks accumulate at the owners
