@@ -371,9 +371,12 @@ def main():
 
     # max over ranks
     t = torch.tensor([ms, ms_e2e, gemm_ms], dtype=torch.float64, device=dev)
+    t_min = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
     ms, ms_e2e, gemm_ms = t.tolist()
+    gemm_ms_fastest_rank = t_min[2].item()   # the ranks run in lockstep (one barrier per step): the spread shows in the kernels
 
     if rank == 0:
         peaks = _peaks()
@@ -404,7 +407,8 @@ def main():
                          "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                          "frac_of_burst_peak": achieved / peaks["tflops_burst"],
                          "step_frac": flops_step / (ms / args.steps * 1e-3) / 1e12 / peak,
-                         "rowloss_ms_per_step": rowloss_ms},
+                         "rowloss_ms_per_step": rowloss_ms,
+                         "kernel_ms_per_step_fastest_rank": gemm_ms_fastest_rank},
             "cpu_baseline": cpu_base,
             "salun_hbm_roofline": salun_res,
             "clocks": clocks,
