@@ -83,28 +83,65 @@ __device__ __forceinline__ int find_segment(const int64_t* off, int n_segs, int6
   return lo;
 }
 
-// bf16 sums have 8 significant bits, so their fp16 keys are multiples of 8: taken as they are, the
-// populated bins of the shared histogram would all live in 4 of the 32 banks.  The low 3 bits are
-// rotated to the top of the shared-memory index, which makes the populated bins contiguous.
-__device__ __forceinline__ uint32_t bin_slot(uint32_t key) { return (key >> 3) | ((key & 7u) << 12); }
-__device__ __forceinline__ uint32_t slot_bin(uint32_t slot) { return ((slot & 0xFFFu) << 3) | (slot >> 12); }
-
+// The histogram is taken over the 32768 bf16 MAGNITUDE patterns (raw bits & 0x7FFF: no conversion per element), and the
+// bins are mapped to their fp16 keys when a CTA flushes: the key is a monotone function of the pattern (many patterns share
+// key 0 and the key of infinity), so  hist_key[key(m)] += hist_pattern[m]  gives exactly the histogram of the keys.
 constexpr int kHistThreads = 1024;
 constexpr int kHistUnroll = 4;  // 128-bit loads in flight per thread
+// Lane-private window.  A warp's 32 shared-memory atomics into random bins cost an expected 3.4 bank-conflict passes (plus
+// same-address serialisation: gradients populate only a few hundred bins).  The bulk of a tensor's |g| values lies within
+// a few octaves, so the kWinSlots patterns around the tensor's typical magnitude (estimated per CTA and tensor from the
+// first 1024 vectors of the slice; any estimate is correct, a poor one is only slow) get one counter PER LANE: pattern m
+// of lane l lives in bank l, and the atomic of an in-window pattern never conflicts within the warp.  Patterns outside the
+// window take the shared bins.
+constexpr int kWinSlots = 512;                       // 4 octaves of bf16 magnitudes (128 patterns per octave)
+constexpr int kWinWords = kWinSlots * 32;            // 64 KB
+constexpr int kHistSmemBytes = (kBins + kWinWords) * 4;
 
 __global__ void __launch_bounds__(kHistThreads) histogram_kernel(const __nv_bfloat16* acc, const int64_t* seg_off, int n_segs,
                                                                  int64_t n_total, int64_t per_block, uint32_t* hist) {
   extern __shared__ uint32_t sh[];
-  for (int b = threadIdx.x; b < kBins; b += kHistThreads) sh[b] = 0;
+  uint32_t* win = sh + kBins;
+  __shared__ unsigned long long est[2];  // (sum of sampled patterns, number of samples)
+  __shared__ int win_base_sh;
+  for (int b = threadIdx.x; b < kBins + kWinWords; b += kHistThreads) sh[b] = 0;
+  if (threadIdx.x < 2) est[threadIdx.x] = 0;
   __syncthreads();
   int64_t pos = (int64_t)blockIdx.x * per_block;
   const int64_t end = min(pos + per_block, n_total);
   if (pos >= end) return;
+  const uint32_t lane = threadIdx.x & 31;
   int seg = find_segment(seg_off, n_segs, pos);
   while (pos < end) {
     while (seg_off[seg + 1] <= pos) ++seg;  // skips empty tensors
     const int64_t stop = min(end, seg_off[seg + 1]);
     const int64_t v1 = stop >> 3;
+    {  // window placement: mean pattern of one sampled element per thread (zeros excluded), minus half a window
+      const int64_t v = (pos >> 3) + threadIdx.x;
+      unsigned ssum = 0, scnt = 0;
+      if (v < v1) {
+        const uint32_t m = (uint32_t)__bfloat16_as_ushort(acc[v << 3]) & 0x7FFFu;
+        if (m) { ssum = m; scnt = 1; }
+      }
+      ssum = __reduce_add_sync(0xffffffffu, ssum);
+      scnt = __reduce_add_sync(0xffffffffu, scnt);
+      if (lane == 0 && scnt) { atomicAdd(&est[0], (unsigned long long)ssum); atomicAdd(&est[1], (unsigned long long)scnt); }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int base = est[1] ? (int)(est[0] / est[1]) - kWinSlots / 2 : 0;
+        base = max(0, min(base, kBins - kWinSlots));
+        win_base_sh = base;
+        est[0] = est[1] = 0;
+      }
+      __syncthreads();
+    }
+    const uint32_t win_base = (uint32_t)win_base_sh;
+    // index of pattern m: the lane's private counter (bank = lane) inside the window, the shared bin outside; no branch
+    auto count = [&](uint32_t m) {
+      const uint32_t rel = m - win_base;
+      const uint32_t idx = (rel < (uint32_t)kWinSlots) ? (uint32_t)kBins + rel * 32u + lane : m;
+      atomicAdd(&sh[idx], 1u);
+    };
     for (int64_t v0 = (pos >> 3) + threadIdx.x; v0 < v1; v0 += (int64_t)kHistThreads * kHistUnroll) {
       uint4 raw[kHistUnroll];
 #pragma unroll
@@ -116,18 +153,33 @@ __global__ void __launch_bounds__(kHistThreads) histogram_kernel(const __nv_bflo
       for (int u = 0; u < kHistUnroll; ++u) {
         const int64_t v = v0 + (int64_t)u * kHistThreads;
         if (v < v1) {
-          uint32_t k[8];
-          keys8(raw[u], k);
+          const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) atomicAdd(&sh[bin_slot(k[j])], 1u);
+          for (int q = 0; q < 4; ++q) {
+            count(w[q] & 0x7FFFu);
+            count((w[q] >> 16) & 0x7FFFu);
+          }
         }
       }
+    }
+    __syncthreads();
+    // fold the window into the shared bins (thread t sums the 32 lane counters of slot t, skewed so that a warp's reads
+    // of one step fall into 32 different banks), then flush the populated bins to the bins of their fp16 keys
+    for (int t = threadIdx.x; t < kWinSlots; t += kHistThreads) {
+      uint32_t c = 0;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        const int ll = (l + t) & 31;
+        c += win[t * 32 + ll];
+        win[t * 32 + ll] = 0;
+      }
+      if (c) sh[win_base + t] += c;
     }
     __syncthreads();
     uint32_t* out = hist + (size_t)seg * kBins;
     for (int b = threadIdx.x; b < kBins; b += kHistThreads) {
       const uint32_t c = sh[b];
-      if (c) { atomicAdd(&out[slot_bin(b)], c); sh[b] = 0; }
+      if (c) { atomicAdd(&out[sal_key(__ushort_as_bfloat16((unsigned short)b))], c); sh[b] = 0; }
     }
     __syncthreads();
     pos = stop;
@@ -666,14 +718,14 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
   if (reinterpret_cast<uintptr_t>(acc) & 15) return fail(CLEAR_ERR_ALIGN, "clear_saliency_histogram: acc must be 16-byte aligned");
   static bool configured = false;
   if (!configured) {
-    CLEAR_CUDA_OK(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBins * 4));
+    CLEAR_CUDA_OK(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     configured = true;
   }
   const int sms = device_sm_count();
   int64_t blocks = sms > 0 ? sms : 148;
   int64_t per_block = ((n_total + blocks - 1) / blocks + 4095) / 4096 * 4096;
   blocks = (n_total + per_block - 1) / per_block;
-  histogram_kernel<<<(unsigned)blocks, kHistThreads, kBins * 4, static_cast<cudaStream_t>(stream)>>>(
+  histogram_kernel<<<(unsigned)blocks, kHistThreads, kHistSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(acc), seg_offsets_dev, n_segs, n_total, per_block, hist);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;

@@ -289,3 +289,28 @@ def test_mask_files_round_trip_into_the_optimizer(tmp_path):
         assert torch.equal(pa, pb), n
         frozen = raw[n].to(dev) == 0
         assert frozen.any() and not torch.equal(pa, torch.zeros_like(pa))
+
+
+def test_histogram_over_every_bf16_pattern():
+    """The histogram is taken over bf16 magnitude patterns and mapped to fp16 keys at flush time: every one of the 65536
+    bf16 bit patterns except the NaNs (two tensors, so that the lane-private window sits at different places), against
+    np.bincount of the oracle's keys."""
+    import ctypes as C
+    from multimodal_unlearning_b200 import _lib, salun
+    dev = torch.device("cuda:0")
+    pats = torch.arange(0x10000, dtype=torch.int32)
+    finite_or_inf = (pats & 0x7FFF) <= 0x7F80
+    allp = pats[finite_or_inf].to(torch.int16).view(torch.bfloat16)
+    g = torch.Generator().manual_seed(9)
+    bulk = (1e-3 * torch.randn(200_000, generator=g)).to(torch.bfloat16)
+    named = {"all": torch.cat([allp, allp, bulk]), "tiny": torch.cat([allp, (1e-30 * torch.randn(50_000, generator=g)).to(torch.bfloat16)])}
+    layout = salun.FlatLayout([(n, v.shape) for n, v in named.items()])
+    state = salun.SaliencyState(layout, dev)
+    state.accumulate_flat(_flat(layout, named, torch.bfloat16).to(dev))
+    state.select((0.5,))
+    hist = state.hist.cpu().numpy()
+    for i, n in enumerate(layout.names):
+        want = np.bincount(SO.saliency_keys(named[n]), minlength=32768)
+        pad = layout.offsets[i + 1] - layout.offsets[i] - layout.numels[i]     # zero padding of the flat layout counts as key 0
+        want[0] += pad
+        assert np.array_equal(hist[i].astype(np.int64), want), n
