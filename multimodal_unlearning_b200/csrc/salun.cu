@@ -94,12 +94,12 @@ constexpr int kHistUnroll = 4;  // 128-bit loads in flight per thread
 // first 1024 vectors of the slice; any estimate is correct, a poor one is only slow) get one counter PER LANE: pattern m
 // of lane l lives in bank l, and the atomic of an in-window pattern never conflicts within the warp.  Patterns outside the
 // window take the shared bins.
-constexpr int kWinSlots = 512;                       // 4 octaves of bf16 magnitudes (128 patterns per octave)
-constexpr int kWinWords = kWinSlots * 32;            // 64 KB
+constexpr int kWinSlots = 768;                       // 6 octaves of bf16 magnitudes (128 patterns per octave)
+constexpr int kWinWords = kWinSlots * 32;            // 96 KB (+ 128 KB of shared bins: 224 of the 227 KB an SM offers)
 constexpr int kHistSmemBytes = (kBins + kWinWords) * 4;
 
 __global__ void __launch_bounds__(kHistThreads) histogram_kernel(const __nv_bfloat16* acc, const int64_t* seg_off, int n_segs,
-                                                                 int64_t n_total, int64_t per_block, uint32_t* hist) {
+                                                                 int64_t n_total, int64_t per_block, uint32_t* hist, int win_slots) {
   extern __shared__ uint32_t sh[];
   uint32_t* win = sh + kBins;
   __shared__ unsigned long long est[2];  // (sum of sampled patterns, number of samples)
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kHistThreads) histogram_kernel(const __nv_bflo
     // index of pattern m: the lane's private counter (bank = lane) inside the window, the shared bin outside; no branch
     auto count = [&](uint32_t m) {
       const uint32_t rel = m - win_base;
-      const uint32_t idx = (rel < (uint32_t)kWinSlots) ? (uint32_t)kBins + rel * 32u + lane : m;
+      const uint32_t idx = (rel < (uint32_t)win_slots) ? (uint32_t)kBins + rel * 32u + lane : m;
       atomicAdd(&sh[idx], 1u);
     };
     for (int64_t v0 = (pos >> 3) + threadIdx.x; v0 < v1; v0 += (int64_t)kHistThreads * kHistUnroll) {
@@ -726,7 +726,8 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
   int64_t per_block = ((n_total + blocks - 1) / blocks + 4095) / 4096 * 4096;
   blocks = (n_total + per_block - 1) / per_block;
   histogram_kernel<<<(unsigned)blocks, kHistThreads, kHistSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(acc), seg_offsets_dev, n_segs, n_total, per_block, hist);
+      static_cast<const __nv_bfloat16*>(acc), seg_offsets_dev, n_segs, n_total, per_block, hist,
+      getenv("CLEAR_HIST_WIN") ? atoi(getenv("CLEAR_HIST_WIN")) : kWinSlots);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }
