@@ -18,6 +18,12 @@ Deliberate differences from the reference:
   * shipped `dpo` returns the IDK per-sequence CE like the reference but skips the three forwards whose
     results the reference discards; `dpo_true=True` evaluates the sigmoid log-ratio instead (#4);
   * `rmu` has no vocabulary head and is not provided.
+
+Work the reference does and this does not, with identical results: CE-type terms run the head on the rows whose shifted
+label is not -100 only (`compact_ignored`; ignored rows contribute nothing to the loss or to any gradient).
+Optional extensions (constructor kwargs, all off by default): `block_rows`, `dpo_true`, `teacher_cache_gb` (replay of the
+frozen teacher's hidden states, teacher_cache.py); `enable_fused_head_allreduce(model)` hands the data-parallel mean of
+d lm_head.weight to the all-reduce fused into the dW contraction.
 """
 from __future__ import annotations
 
