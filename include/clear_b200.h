@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CLEAR_ABI_VERSION 1
+#define CLEAR_ABI_VERSION 2
 
 typedef enum ClearStatus {
   CLEAR_OK = 0,

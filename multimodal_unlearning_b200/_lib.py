@@ -137,8 +137,8 @@ def load() -> C.CDLL:
     lib.clear_head_loss_fwd_bwd.argtypes = [C.POINTER(HeadArgs), C.c_void_p, C.c_size_t, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError here = the .so is stale / does not match include/clear_b200.h
-    if lib.clear_abi_version() != 1:
-        raise RuntimeError(f"libclear_b200.so ABI version {lib.clear_abi_version()} != 1; rebuild the library")
+    if lib.clear_abi_version() != 2:
+        raise RuntimeError(f"libclear_b200.so ABI version {lib.clear_abi_version()} != 2; rebuild the library")
     _lib = lib
     return lib
 
