@@ -569,6 +569,20 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
   return __fsub_rn(p, __fmul_rn(c.step_size, q));   // addcdiv_(exp_avg, denom, -step_size)
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): the eight fp32 moments of a thread's eight parameters are 32
+// contiguous bytes, so one instruction per warp covers 1 KB contiguously instead of two half-used 16-byte accesses at a
+// 32-byte stride.
+__device__ __forceinline__ void ld256(const float* p, float (&x)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(float* p, const float (&x)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]),
+               "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7])
+               : "memory");
+}
+
 constexpr int kAdamVecs = 1;  // 128-bit parameter vectors per thread and iteration (loads issued before any math)
 
 // kPackedMask: `mask` is the bit-packed format (bit i & 7 of byte i >> 3): 22.125 instead of 23 bytes per parameter
@@ -580,7 +594,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
   const float gscale = c.grad_scale ? *c.grad_scale : 1.f;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kAdamVecs) {
     uint4 pr[kAdamVecs], gr[kAdamVecs];
-    float4 m0[kAdamVecs], m1[kAdamVecs], v0[kAdamVecs], v1[kAdamVecs];
+    float mm_[kAdamVecs][8], vv_[kAdamVecs][8];
     uint2 mk[kAdamVecs];
 #pragma unroll
     for (int u = 0; u < kAdamVecs; ++u) {
@@ -588,10 +602,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
       if (i < nvec) {
         pr[u] = reinterpret_cast<const uint4*>(param)[i];
         gr[u] = ld_stream(reinterpret_cast<const uint4*>(grad) + i);
-        m0[u] = reinterpret_cast<const float4*>(exp_avg)[2 * i];
-        m1[u] = reinterpret_cast<const float4*>(exp_avg)[2 * i + 1];
-        v0[u] = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i];
-        v1[u] = reinterpret_cast<const float4*>(exp_avg_sq)[2 * i + 1];
+        ld256(exp_avg + (i << 3), mm_[u]);
+        ld256(exp_avg_sq + (i << 3), vv_[u]);
         if constexpr (kPackedMask) mk[u] = make_uint2(reinterpret_cast<const uint8_t*>(mask)[i], 0u);
         else mk[u] = mask ? *reinterpret_cast<const uint2*>(mask + (i << 3)) : make_uint2(0x01010101u, 0x01010101u);
       }
@@ -602,8 +614,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
       if (i >= nvec) break;
       __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(&pr[u]);
       const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&gr[u]);
-      float mm[8] = {m0[u].x, m0[u].y, m0[u].z, m0[u].w, m1[u].x, m1[u].y, m1[u].z, m1[u].w};
-      float vv[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+      float (&mm)[8] = mm_[u];
+      float (&vv)[8] = vv_[u];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t mb = kPackedMask ? ((mk[u].x >> j) & 1u) : (((j < 4 ? mk[u].x : mk[u].y) >> (8 * (j & 3))) & 0xFFu);
@@ -612,10 +624,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(__nv_bfloat16* param, const 
         ph[j] = __float2bfloat16_rn(adam_one(__bfloat162float(ph[j]), g, mm[j], vv[j], c));
       }
       reinterpret_cast<uint4*>(param)[i] = pr[u];
-      reinterpret_cast<float4*>(exp_avg)[2 * i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-      reinterpret_cast<float4*>(exp_avg)[2 * i + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
-      reinterpret_cast<float4*>(exp_avg_sq)[2 * i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-      reinterpret_cast<float4*>(exp_avg_sq)[2 * i + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+      st256(exp_avg + (i << 3), mm);
+      st256(exp_avg_sq + (i << 3), vv);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -785,6 +795,8 @@ int clear_masked_adamw(const ClearAdamWArgs* a, void* stream) {
   if ((reinterpret_cast<uintptr_t>(a->param) | reinterpret_cast<uintptr_t>(a->grad) | reinterpret_cast<uintptr_t>(a->exp_avg) |
        reinterpret_cast<uintptr_t>(a->exp_avg_sq)) & 15)
     return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: tensors must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(a->exp_avg) | reinterpret_cast<uintptr_t>(a->exp_avg_sq)) & 31)
+    return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: the fp32 moments must be 32-byte aligned (256-bit accesses)");
   if (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)) return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: mask must be 8-byte aligned");
   if (a->mask && a->mask_bits) return fail(CLEAR_ERR_KIND, "clear_masked_adamw: pass mask or mask_bits, not both");
   // Scalar prologue of torch.optim.adam._single_tensor_adam, in double like the Python floats there.
