@@ -136,14 +136,15 @@ def test_rowloss_vs_closed_forms(kind, v):
     assert (z[:, v:] == 0).all(), "padding columns must be zeroed"
 
 
-@pytest.mark.parametrize("v", [13, 1003, 32064, 40000])
-def test_npo_beta_one_kernel(v):
+@pytest.mark.parametrize("v,n", [(13, 70), (1003, 70), (1000, 70), (1000, 700), (32064, 70), (32064, 333), (24576, 200), (40000, 70)])
+def test_npo_beta_one_kernel(v, n):
     """The shipped NPO recipe (loss_beta = 1, config/mm/forget.yaml:40) runs its own row kernel (batched reciprocal /
     logarithm, s cached in shared memory): ragged vocabularies (13, 1003), the BASELINE vocabulary, and one wider than
-    the shared-memory cache and the single-round-trip statistics merge (40000 = 157 column tiles)."""
+    the shared-memory cache and the single-round-trip statistics merge (40000 = 157 column tiles).  Vocabularies that are
+    Row counts below and above the SM count, a row that fits the s-cache exactly (24576)."""
     from multimodal_unlearning_b200 import head
     dev = torch.device("cuda:0")
-    n, h = 70, 128
+    h = 128
     hid, w, rh, rw, y = _inputs(n, h, v, 77, dev)
     ld = (v + 63) // 64 * 64
     nt = head.vtiles(v)
