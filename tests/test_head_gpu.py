@@ -405,6 +405,12 @@ def _torch_reference_fullsize(kind, hid, w, rh, rw, y, beta, chunk=1024):
             d[torch.arange(d.shape[0], device=d.device), yy.clamp(min=0)] -= 1
             d = d * valid[:, None] / m
             total += rows.double().sum() / m
+        elif kind == HO.KIND_KL_FWD:   # kl_div(student_logp, teacher_logp, batchmean, log_target): all rows / N
+            zr = (rh[r0:r0 + chunk].float() @ rwf.t()).to(torch.bfloat16).float()
+            lq = torch.log_softmax(zr, -1)
+            q = lq.exp()
+            total += (q * (lq - lp)).double().sum() / n
+            d = (p - q) / n
         else:  # NPO
             zr = (rh[r0:r0 + chunk].float() @ rwf.t()).to(torch.bfloat16).float()
             q = torch.softmax(zr, -1)
@@ -417,9 +423,11 @@ def _torch_reference_fullsize(kind, hid, w, rh, rw, y, beta, chunk=1024):
     return total, dH, dW
 
 
-@pytest.mark.parametrize("kind,n,h,v", [(HO.KIND_NPO, 8192, 4096, 32064), (HO.KIND_CE, 8192, 4096, 32000)])
+@pytest.mark.parametrize("kind,n,h,v", [(HO.KIND_NPO, 8192, 4096, 32064), (HO.KIND_CE, 8192, 4096, 32000),
+                                        (HO.KIND_KL_FWD, 8192, 4096, 32064)])
 def test_baseline_size_parity(kind, n, h, v):
-    """BASELINE.json configs[1] (NPO, bs 8 x seq 1024, LLaVA-1.5-7B head) and configs[4] (grad_ascent, bs 16 x 512)."""
+    """BASELINE.json configs[1] (NPO, bs 8 x seq 1024, LLaVA-1.5-7B head), configs[4] (grad_ascent, bs 16 x 512) and the
+    KL-retain split of configs[2] (bs 4 x seq 2048)."""
     from multimodal_unlearning_b200 import head
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(5)
@@ -447,7 +455,7 @@ def test_baseline_size_parity(kind, n, h, v):
     rows, dterm = HO.rowloss(kind, z.double(), zr.double(), y[idx.to(dev)].cpu(), 1.0)
     got_rows = res.loss_rows[idx.to(dev)].double().cpu()
     assert (got_rows - rows).abs().max().item() <= LOSS_RTOL * rows.abs().max().item()
-    scale = (1.0 / (y != -100).sum().item()) if kind == HO.KIND_CE else 2.0 / (n * v)
+    scale = {HO.KIND_CE: 1.0 / (y != -100).sum().item(), HO.KIND_KL_FWD: 1.0 / n}.get(kind, 2.0 / (n * v))
     want_rows_dh = (dterm * scale) @ w.double().cpu()
     assert _rel(res.dhidden[idx.to(dev)], want_rows_dh) <= GRAD_RTOL
 
