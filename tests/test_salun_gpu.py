@@ -314,3 +314,60 @@ def test_histogram_over_every_bf16_pattern():
         pad = layout.offsets[i + 1] - layout.offsets[i] - layout.numels[i]     # zero padding of the flat layout counts as key 0
         want[0] += pad
         assert np.array_equal(hist[i].astype(np.int64), want), n
+
+
+def test_full_llama7b_parameter_list_properties():
+    """BASELINE configs[3] size: all 291 tensors / 6.74 B parameters of Llama-2-7B.  Far beyond the CPU sort, so
+    order-statistic properties: exactly int(th * numel) ones per tensor, masks nested across thresholds, the bit-packed
+    mask equal to the packed int8 mask, and the masked update touching exactly the selected parameters."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+    import bench_salun
+    from multimodal_unlearning_b200 import salun
+    dev = torch.device("cuda:0")
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs the B200's 180 GB")
+    lay = salun.FlatLayout(bench_salun.llama7b_shapes(32))
+    assert len(lay.names) == 291 and lay.total == 6738415616
+    st = salun.SaliencyState(lay, dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    for o in range(0, lay.total, 1 << 28):
+        n = min(1 << 28, lay.total - o)
+        st.acc[o:o + n] = (1e-3 * torch.randn(n, generator=g, device=dev)).to(torch.bfloat16)
+    ths = (0.1, 0.5)
+    sel = st.select(ths)
+    m10 = st.mask_flat(sel, 0)
+    m50 = st.mask_flat(sel, 1)
+    assert int(((m10 == 1) & (m50 == 0)).sum().item()) == 0                      # nested
+    numels = torch.tensor(lay.numels, dtype=torch.int64)
+    offs = lay.offsets
+    for m, th in ((m10, 0.1), (m50, 0.5)):
+        per8 = m.view(-1, 8).sum(1, dtype=torch.int32)                                    # ones per 8-element group
+        csum = torch.cumsum(per8, 0, dtype=torch.int64)                                   # ones up to every group boundary
+        del per8
+        ends = torch.tensor([(offs[i] + (lay.numels[i] + 7) // 8 * 8) // 8 - 1 for i in range(len(lay.names))], device=dev)
+        starts = torch.tensor([offs[i] // 8 - 1 for i in range(len(lay.names))], device=dev)
+        upto = csum[ends]
+        before = torch.where(starts >= 0, csum[starts.clamp(min=0)], torch.zeros_like(upto))
+        counts = (upto - before).cpu()
+        want = torch.tensor([int(th * n) for n in lay.numels], dtype=torch.int64)
+        assert torch.equal(counts, want), th
+        del csum
+    bits = st.mask_flat(sel, 1, packed=True)
+    assert torch.equal(salun.pack_mask(m50), bits)             # converter kernel vs direct bit-packed output
+    step = 1 << 27                                               # and against torch, slice by slice
+    weights = (2 ** torch.arange(8, device=dev, dtype=torch.int16)).view(1, 8)
+    for o in range(0, lay.total, step):
+        sl = m50[o:o + step].view(-1, 8).to(torch.int16)
+        assert torch.equal((sl * weights).sum(1).to(torch.uint8), bits[o // 8:(o + step) // 8])
+    del m10
+    # masked update: parameters outside the mask only see the weight decay, parameters inside move
+    p = torch.ones(lay.total, dtype=torch.bfloat16, device=dev)
+    mom = torch.zeros(lay.total, dtype=torch.float32, device=dev)
+    var = torch.zeros(lay.total, dtype=torch.float32, device=dev)
+    salun.masked_adamw_flat(p, st.acc, mom, var, bits, 1, lr=1e-2, weight_decay=0.0)
+    moved = p != 1
+    sel_nonzero = (m50 == 1) & (st.acc != 0)
+    assert torch.equal(moved, sel_nonzero)
+    assert int((mom != 0).sum().item()) == int(sel_nonzero.sum().item())
