@@ -31,9 +31,9 @@ KIND_NAMES = {KIND_CE: "ce", KIND_KL_FWD: "kl_fwd", KIND_KL_REV: "kl_rev", KIND_
 _NEEDS_REF = (KIND_KL_FWD, KIND_KL_REV, KIND_NPO)
 
 # Rows staged per pass.  8192 rows x 32064 bf16 = 525 MB per projected operand, small against 180 GB of HBM3e.
-# Measured on B200 under the 1 kW power cap (tools/gpu_probe2.py, interleaved A/B, NPO step at N = 8192):
-# 8192-row blocks 7.13 ms, 4096-row blocks 7.42 ms (7.20 ms with the two-stream overlap), 2048-row blocks 8.30 ms —
-# fewer blocks mean fewer read-modify-write passes over dW and fuller waves of output tiles in the dH contraction.
+# Measured on B200 under the 1 kW power cap (bench.py --block-rows, final build of round 1, NPO step at N = 8192):
+# 8192-row blocks 6.46 ms, 4096-row blocks 6.93 ms, 2048-row blocks 7.43 ms — fewer blocks mean fewer re-reads of W,
+# fewer read-modify-write passes over dW and fuller waves of output tiles in the dH contraction.
 DEFAULT_BLOCK_ROWS = 8192
 # Up to this many row blocks accumulate dW directly in bf16; beyond it an fp32 accumulator is used and converted once.
 MAX_BF16_ACCUM_BLOCKS = 4
