@@ -136,7 +136,6 @@ def cpu_reference_rate(sample_rows: int, reps: int):
 def cpu_salun_rate(n_elems: int = 1 << 24):
     """parameters/s of the reference's per-tensor, per-threshold mask (generate_mask.py:61-72: fp16 |grad| keys, descending
     sort, top-k -> int8) on the host, restated by the oracle (stable sort), on a slice of n_elems synthetic gradients."""
-    import numpy as np
     import torch
     from oracle import salun_oracle as SO
 
