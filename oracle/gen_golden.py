@@ -172,9 +172,55 @@ def gen_salun():
     print(f"salun: {len(names)} tensors, {n_total} elements, 3 batches, 10 thresholds")
 
 
+REG_L1, REG_L0 = 1e-4, 1e-6
+REG_PROBES = ("model.language_model.norm.weight", "model.norm.weight", "lm_head.weight")
+
+
+def gen_regulariser():
+    """L1 / L0 weight regulariser (mm/trainer.py:451-481, nlp/dataloader.py:461-483) through the reference's own
+    compute_loss: the same step with and without the lambdas, for l_norm_from = zero / init (mm) and the nlp variant
+    (always relative to the oracle model).  Stored: both losses and, for a few parameters, grad(with) - grad(without)."""
+    def grads(model):
+        return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    out = {"l1_lambda": np.float64(REG_L1), "l0_lambda": np.float64(REG_L0)}
+    student = RH.tiny_llava(0)
+    teacher = RH.perturbed_copy(student, 5)
+    inputs = {"retain": RH.mm_split(2, 32, 11), "forget": RH.mm_split(2, 32, 12), "idk": RH.mm_split(2, 32, 13)}
+    plain = RH.run_mm("grad_ascent", student, teacher, {k: dict(v) for k, v in inputs.items()})
+    g0 = grads(student)
+    for origin in ("zero", "init"):
+        res = RH.run_mm("grad_ascent", student, teacher, {k: dict(v) for k, v in inputs.items()}, l1_lambda=REG_L1,
+                        l0_lambda=REG_L0, l_norm_from=origin)
+        g1 = grads(student)
+        out[f"mm_{origin}_loss_plain"] = plain["loss"].double().numpy()
+        out[f"mm_{origin}_loss_reg"] = res["loss"].double().numpy()
+        for n in g1:
+            if n in REG_PROBES:
+                d = (g1[n] - g0[n]).float()
+                out[f"mm_{origin}_dgrad::{n}"] = (d[:64] if d.dim() == 2 else d).numpy()
+    student = RH.tiny_llama(0)
+    teacher = RH.perturbed_copy(student, 5)
+    triples = [RH.nlp_triple(2, 32, 21), RH.nlp_triple(2, 32, 22), RH.nlp_triple(2, 32, 23)]
+    plain = RH.run_nlp("grad_ascent", student, teacher, triples)
+    g0 = grads(student)
+    res = RH.run_nlp("grad_ascent", student, teacher, triples, l1_lambda=REG_L1, l0_lambda=REG_L0)
+    g1 = grads(student)
+    out["nlp_loss_plain"] = plain["loss"].double().numpy()
+    out["nlp_loss_reg"] = res["loss"].double().numpy()
+    for n in g1:
+        if n in REG_PROBES:
+            d = (g1[n] - g0[n]).float()
+            out[f"nlp_dgrad::{n}"] = (d[:64] if d.dim() == 2 else d).numpy()
+    np.savez_compressed(GOLDEN / "regulariser.npz", **out)
+    print("regulariser:", {k: float(v) for k, v in out.items() if "loss" in k})
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = set(sys.argv[1:]) or {"mm", "nlp", "salun"}
+    which = set(sys.argv[1:]) or {"mm", "nlp", "salun", "reg"}
+    if "reg" in which:
+        gen_regulariser()
     if "mm" in which:
         gen_mm()
     if "nlp" in which:

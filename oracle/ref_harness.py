@@ -166,7 +166,8 @@ class HeadCapture:
         return model.lm_head.register_forward_pre_hook(pre)
 
 
-def run_mm(loss_type: str, student, teacher, inputs: dict, beta: float = 1.0, loss_args=None):
+def run_mm(loss_type: str, student, teacher, inputs: dict, beta: float = 1.0, loss_args=None, l1_lambda: float = 0.0,
+           l0_lambda: float = 0.0, l_norm_from: str = "zero"):
     """Reference MMTrainerForgetting.compute_loss + backward; returns loss, captured hidden / dH per
     student forward (in call order), teacher hidden per teacher forward, and dW."""
     MM, _, _, _ = import_reference()
@@ -174,8 +175,8 @@ def run_mm(loss_type: str, student, teacher, inputs: dict, beta: float = 1.0, lo
     hs = cap_s.attach(student)
     ht = cap_t.attach(teacher) if teacher is not None else None
     fake_self = types.SimpleNamespace(
-        loss_type=loss_type.lower(), teacher_model=teacher, loss_beta=beta, l1_lambda=0.0, l0_lambda=0.0,
-        l_norm_from="zero", loss_args=loss_args or {"bad_weight": 2.5, "random_weight": 1.0, "normal_weight": 0.5},
+        loss_type=loss_type.lower(), teacher_model=teacher, loss_beta=beta, l1_lambda=l1_lambda, l0_lambda=l0_lambda,
+        l_norm_from=l_norm_from, loss_args=loss_args or {"bad_weight": 2.5, "random_weight": 1.0, "normal_weight": 0.5},
         is_deepspeed_enabled=False, to_device=MM.MMTrainerForgetting.to_device)
     student.zero_grad(set_to_none=True)
     student.train()
@@ -195,13 +196,14 @@ def run_mm(loss_type: str, student, teacher, inputs: dict, beta: float = 1.0, lo
     }
 
 
-def run_nlp(loss_type: str, student, oracle_model, inputs: list, beta: float = 1.0):
+def run_nlp(loss_type: str, student, oracle_model, inputs: list, beta: float = 1.0, l1_lambda: float = 0.0,
+            l0_lambda: float = 0.0):
     _, _, NLP, _ = import_reference()
     cap_s, cap_t = HeadCapture(), HeadCapture()
     hs = cap_s.attach(student)
     ht = cap_t.attach(oracle_model) if oracle_model is not None else None
-    fake_self = types.SimpleNamespace(loss_type=loss_type, oracle_model=oracle_model, loss_beta=beta, l1_lambda=0.0,
-                                      l0_lambda=0.0, is_deepspeed_enabled=False,
+    fake_self = types.SimpleNamespace(loss_type=loss_type, oracle_model=oracle_model, loss_beta=beta, l1_lambda=l1_lambda,
+                                      l0_lambda=l0_lambda, is_deepspeed_enabled=False,
                                       to_device=NLP.CustomTrainerForgetting.to_device)
     student.zero_grad(set_to_none=True)
     student.train()

@@ -168,3 +168,33 @@ def test_norm_oracles_match_the_torch_calls_the_reference_makes():
     l1z, l0z = SO.param_l1l0(a)
     assert abs(l1z - torch.norm(torch.cat([x.view(-1) for x in a]).float(), p=1).item()) <= 1e-5 * l1z
     assert l0z == sum(int((x != 0).sum()) for x in a)
+
+
+def test_regulariser_oracle_matches_the_reference_compute_loss():
+    """tests/golden/regulariser.npz = the reference's own compute_loss with and without l1_lambda / l0_lambda
+    (oracle/gen_golden.py gen_regulariser): the oracle's L1 / L0 terms explain the loss difference, and the gradient
+    difference is l1_lambda * sign(p - origin) — for l_norm_from = zero / init (mm) and the nlp variant (vs the oracle model)."""
+    from oracle import ref_harness as RH
+    z = np.load(GOLDEN / "regulariser.npz")
+    l1, l0 = float(z["l1_lambda"]), float(z["l0_lambda"])
+    cases = [("mm_zero", RH.tiny_llava, False), ("mm_init", RH.tiny_llava, True), ("nlp", RH.tiny_llama, True)]
+    for tag, make, vs_teacher in cases:
+        student = make(0)
+        teacher = RH.perturbed_copy(student, 5)
+        params = [p for p in student.parameters() if p.requires_grad]
+        refs = [tp for p, tp in zip(student.parameters(), teacher.parameters()) if p.requires_grad] if vs_teacher else None
+        n1, n0 = SO.param_l1l0(params, refs)
+        want = float(z[f"{tag}_loss_reg"]) - float(z[f"{tag}_loss_plain"])
+        got = l1 * n1 + l0 * n0
+        assert abs(got - want) <= 2e-4 * abs(want), (tag, got, want)       # the reference sums 8.65 M fp32 terms in fp32
+        named = dict(student.named_parameters())
+        tnamed = dict(teacher.named_parameters())
+        probes = [k for k in z.files if k.startswith(f"{tag}_dgrad::")]
+        assert probes
+        for k in probes:
+            name = k.split("::", 1)[1]
+            d = named[name].detach() - (tnamed[name].detach() if vs_teacher else 0)
+            sign = torch.sign(d)
+            sign = sign[:64] if sign.dim() == 2 else sign
+            got_d = torch.from_numpy(z[k])
+            assert torch.allclose(got_d, l1 * sign, atol=2e-6), (tag, name)   # fp32 gradient difference of two backward runs
