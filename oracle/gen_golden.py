@@ -95,6 +95,22 @@ def gen_mm(length_default: int = 32):
         print(f"mm  {lt:40s} loss {float(res['loss']):+.6f}")
 
 
+def gen_mm_dpo_true(length: int = 32):
+    """head_mm_dpo_true.npz: value and gradients of the DPO expression the reference computes and overwrites."""
+    student = RH.tiny_llava(0)
+    teacher = RH.perturbed_copy(student, 5)
+    with torch.no_grad():
+        teacher.lm_head.weight.copy_(teacher_head_weight())
+    inputs = {"retain": RH.mm_split(2, length, 11), "forget": RH.mm_split(2, length, 12), "idk": RH.mm_split(2, length, 13)}
+    names_s, names_t = HO.MM_CALL_ORDER["dpo"]
+    res = RH.run_mm_dpo_true(student, teacher, {k: dict(v) for k, v in inputs.items()})
+    assert len(res["hidden"]) == len(names_s) and len(res["ref_hidden"]) == len(names_t)
+    labels = [inputs[n]["labels"] for n in names_s]
+    out = pack(res, labels, names_s, names_t, probe_rows(labels[0], 3), 0.1)
+    np.savez(GOLDEN / "head_mm_dpo_true.npz", **out)
+    print(f"mm  {'dpo_true':40s} loss {float(res['loss']):+.6f}")
+
+
 def gen_nlp(length: int = 32):
     student = RH.tiny_llama(0)
     teacher = RH.perturbed_copy(student, 5)
@@ -223,6 +239,8 @@ def main():
         gen_regulariser()
     if "mm" in which:
         gen_mm()
+    if "mm" in which or "dpo_true" in which:
+        gen_mm_dpo_true()
     if "nlp" in which:
         gen_nlp()
     if "salun" in which:

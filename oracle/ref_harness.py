@@ -221,3 +221,47 @@ def run_nlp(loss_type: str, student, oracle_model, inputs: list, beta: float = 1
         "ref_hidden": [h.detach() for h in cap_t.hidden],
         "dweight": student.lm_head.weight.grad.detach().clone(),
     }
+
+
+def run_mm_dpo_true(student, teacher, inputs: dict):
+    """The DPO sigmoid log-ratio the reference evaluates and then overwrites (mm/trainer.py:390-394): the unmodified
+    compute_loss("dpo") runs with torch.nn.functional.logsigmoid recording its result; the recorded tensor is still part
+    of the reference's own autograd graph, so -mean of it and its backward are the reference's value and gradients of
+    that expression.  Same return layout as run_mm."""
+    import torch.nn.functional as F
+
+    MM, _, _, _ = import_reference()
+    cap_s, cap_t = HeadCapture(), HeadCapture()
+    hs = cap_s.attach(student)
+    ht = cap_t.attach(teacher)
+    fake_self = types.SimpleNamespace(
+        loss_type="dpo", teacher_model=teacher, loss_beta=1.0, l1_lambda=0.0, l0_lambda=0.0, l_norm_from="zero", loss_args={},
+        is_deepspeed_enabled=False, to_device=MM.MMTrainerForgetting.to_device)
+    student.zero_grad(set_to_none=True)
+    student.train()
+    recorded = []
+    real = F.logsigmoid
+
+    def spy(x, *a, **kw):
+        out = real(x, *a, **kw)
+        recorded.append(out)
+        return out
+
+    F.logsigmoid = spy
+    try:
+        MM.MMTrainerForgetting.compute_loss(fake_self, Wrap(student), inputs)
+        assert len(recorded) == 1, "the reference calls logsigmoid exactly once in the dpo branch"
+        loss = -recorded[0].mean()
+        loss.backward()
+    finally:
+        F.logsigmoid = real
+        hs.remove()
+        ht.remove()
+    return {
+        "loss": loss.detach(),
+        "hidden": [h.detach() for h in cap_s.hidden],
+        "dhidden": [h.grad.detach() if h.grad is not None else None for h in cap_s.hidden],
+        "ref_hidden": [h.detach() for h in cap_t.hidden],
+        "dweight": student.lm_head.weight.grad.detach().clone(),
+    }
+

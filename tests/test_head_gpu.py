@@ -318,8 +318,9 @@ def _run_recipe(case: HeadCase, dev):
             ys = torch.stack([lab[n] for n in rnd], dim=1)  # [B, K, L]
             ids = torch.stack([tag(n, lab[n]) for n in rnd], dim=1)
             inputs["random"] = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": ys}
-        fake = types.SimpleNamespace(loss_type=case.loss_type.lower(), teacher_model=teacher, loss_beta=case.beta,
-                                     l1_lambda=0.0, l0_lambda=0.0, l_norm_from="zero",
+        true_dpo = case.loss_type == "dpo_true"   # the flagged extension: same `dpo` recipe, sigmoid log-ratio kept
+        fake = types.SimpleNamespace(loss_type="dpo" if true_dpo else case.loss_type.lower(), teacher_model=teacher,
+                                     loss_beta=case.beta, l1_lambda=0.0, l0_lambda=0.0, l_norm_from="zero", dpo_true=true_dpo,
                                      loss_args={"bad_weight": 2.5, "random_weight": 1.0, "normal_weight": 0.5})
         loss = T.MMTrainerForgetting.compute_loss(fake, student, inputs)
     else:
@@ -350,13 +351,16 @@ def _run_recipe(case: HeadCase, dev):
 def _oracle_on_bf16(case: HeadCase):
     student, teacher, w, wr = case.oracle_inputs(cast=torch.bfloat16)
     fn = HO.mm_compute_loss if case.trainer == "mm" else HO.nlp_compute_loss
+    if case.loss_type == "dpo_true":
+        fn = lambda student, weight, teacher=None, ref_weight=None, beta=1.0, loss_type=None, logits_dtype=None: \
+            HO.dpo_true(student, weight, teacher, ref_weight, beta=0.1, logits_dtype=logits_dtype)
     if case.trainer == "nlp" and case.loss_type == "npo":
         fn = HO.mm_compute_loss  # App. B #3: the nlp formula is NaN by construction; the product evaluates the mm one
     return HO.loss_and_grads(fn, student, w, teacher=teacher, ref_weight=wr, beta=case.beta, loss_type=case.loss_type,
                              logits_dtype=torch.bfloat16)
 
 
-@pytest.mark.parametrize("trainer,loss_type", [("mm", l) for l in MM_LOSSES] + [("nlp", l) for l in NLP_LOSSES])
+@pytest.mark.parametrize("trainer,loss_type", [("mm", l) for l in MM_LOSSES] + [("mm", "dpo_true")] + [("nlp", l) for l in NLP_LOSSES])
 def test_recipes_against_reference_fixtures(trainer, loss_type):
     case = HeadCase(trainer, loss_type)
     dev = torch.device("cuda:0")

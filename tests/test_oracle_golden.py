@@ -43,6 +43,15 @@ def test_mm_oracle_matches_reference(loss_type):
     _check(HeadCase("mm", loss_type), HO.mm_compute_loss)
 
 
+def test_dpo_true_oracle_matches_the_expression_the_reference_discards():
+    """head_mm_dpo_true.npz: the unmodified compute_loss("dpo") with F.logsigmoid recorded — value and gradients of
+    -logsigmoid(0.1 * (pi - ref)).mean() (mm/trainer.py:390-394), which the reference overwrites before returning."""
+    case = HeadCase("mm", "dpo_true")
+    assert abs(case.beta - 0.1) < 1e-12
+    _check(case, lambda student, weight, teacher=None, ref_weight=None, beta=1.0, loss_type=None, logits_dtype=None:
+           HO.dpo_true(student, weight, teacher, ref_weight, beta=0.1, logits_dtype=logits_dtype))
+
+
 @pytest.mark.parametrize("loss_type", NLP_LOSSES)
 def test_nlp_oracle_matches_reference(loss_type):
     _check(HeadCase("nlp", loss_type), HO.nlp_compute_loss)
