@@ -14,7 +14,7 @@
  *   - plain pointers and sizes only; every pointer is a CUDA device pointer unless marked "host";
  *   - the caller owns every buffer (inputs, outputs, workspace); the library frees nothing of the
  *     caller's and keeps no pointer after a call returns.  Its one device allocation is made on the
- *     first contraction on a device: a 4 KB ring of work counters for the dynamic tile scheduler;
+ *     first contraction on a device: a 32 KB ring of work counters for the dynamic tile scheduler;
  *   - all work is enqueued on the cudaStream_t passed in (as a void*); no hidden synchronisation;
  *   - return value: 0 success, <0 a ClearStatus argument/shape error detected before any launch,
  *     >0 a cudaError_t.  clear_last_error() returns a thread-local message for the last failure;

@@ -92,11 +92,11 @@ static int make_output_map(CUtensorMap* tm, void* d, int d_is_f32, int64_t ldd, 
   return 0;
 }
 
-// Work counters of the dynamic tile scheduler: a ring of device words, one per launch in flight (launches on different
-// streams may overlap), allocated once per device on first use — the library's only device allocation — and zeroed on
-// the launching stream right before the kernel.
-static int next_work_counter(cudaStream_t stream, unsigned int** out) {
-  constexpr int kRing = 1024;
+// Work counters of the dynamic tile scheduler: a ring of (claim, finished) word pairs, one pair per launch in flight
+// (launches on different streams may overlap), allocated and zeroed once per device on first use — the library's only
+// device allocation.  A kernel's last CTA group re-arms its pair, so consecutive launches need no memset between them.
+static int next_work_counter(unsigned int** out) {
+  constexpr int kRing = 4096;
   constexpr int kMaxDevices = 64;
   static unsigned int* ring[kMaxDevices] = {};
   static unsigned int cursor[kMaxDevices] = {};
@@ -104,14 +104,14 @@ static int next_work_counter(cudaStream_t stream, unsigned int** out) {
   int dev = 0;
   CLEAR_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDevices) return fail(CLEAR_ERR_DEVICE, "device ordinal %d out of range", dev);
-  unsigned int* slot;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (!ring[dev]) CLEAR_CUDA_OK(cudaMalloc(&ring[dev], kRing * sizeof(unsigned int)));
-    slot = ring[dev] + (cursor[dev]++ % kRing);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ring[dev]) {
+    unsigned int* p = nullptr;
+    CLEAR_CUDA_OK(cudaMalloc(&p, kRing * 2 * sizeof(unsigned int)));
+    CLEAR_CUDA_OK(cudaMemset(p, 0, kRing * 2 * sizeof(unsigned int)));
+    ring[dev] = p;
   }
-  CLEAR_CUDA_OK(cudaMemsetAsync(slot, 0, sizeof(unsigned int), stream));
-  *out = slot;
+  *out = ring[dev] + 2 * (cursor[dev]++ % kRing);
   return 0;
 }
 
@@ -280,7 +280,7 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
     p.k_splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty item
   }
   p.lse_part = reinterpret_cast<float2*>(lse_part);
-  if ((rc = next_work_counter(stream, &p.work_counter))) return rc;
+  if ((rc = next_work_counter(&p.work_counter))) return rc;
   p.n_peers = n_peers;
   p.mtiles_per_peer = n_peers > 0 ? peer_mtiles(cta_group, m, n_peers) : 1;
 

@@ -42,7 +42,9 @@ struct GemmParams {
   int k_splits;          // > 1: each output tile is cut into k_splits work items along K (fp32 reduce-add epilogue)
   int kb_per_split;      // K blocks (of 64) per work item
   float2* lse_part;      // [M][n_tiles] when kEpiStoreBF16Lse
-  unsigned int* work_counter;  // zeroed before the launch: the next unclaimed work item (dynamic tile scheduler)
+  unsigned int* work_counter;  // [0] next unclaimed work item (dynamic tile scheduler), [1] CTA groups that have finished;
+                               // both zero at launch: the last group to finish resets them, so no memset node sits between
+                               // two launches on a stream
   int n_peers;                 // > 0: the output is sharded by M tiles over the peers' buffers (fused reduce-scatter)
   int mtiles_per_peer;         // owner of M tile mt = min(n_peers - 1, mt / mtiles_per_peer)
 };
@@ -409,6 +411,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (acc == 0) acc_phase ^= 1u;
     }
     if (lane == 0) ptx::tma_store_wait<0>();
+  }
+
+  // The producer of the leader CTA has claimed its last item long ago; once every group has reported here, nobody touches
+  // the counters any more and the last one re-arms them for the launch that will reuse this slot of the ring.
+  if (warp == 0 && lane == 0 && cta_rank == 0) {
+    const unsigned int groups = gridDim.x / kCtaGroup;
+    if (atomicAdd(p.work_counter + 1, 1u) == groups - 1) {
+      p.work_counter[0] = 0;
+      p.work_counter[1] = 0;
+      __threadfence();
+    }
   }
 
   // ======================================= teardown ==============================================
