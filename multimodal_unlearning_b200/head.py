@@ -35,6 +35,9 @@ _NEEDS_REF = (KIND_KL_FWD, KIND_KL_REV, KIND_NPO)
 # 8192-row blocks 6.46 ms, 4096-row blocks 6.93 ms, 2048-row blocks 7.43 ms — fewer blocks mean fewer re-reads of W,
 # fewer read-modify-write passes over dW and fuller waves of output tiles in the dH contraction.
 DEFAULT_BLOCK_ROWS = 8192
+# compact_ignored gathers the valid rows only when at most this fraction of the rows is valid: above it the gather / scatter
+# passes (2 x N x H x 2 bytes each way) cost more than the skipped rows save.
+COMPACT_MAX_FRACTION = 0.9
 # Up to this many row blocks accumulate dW directly in bf16; beyond it an fp32 accumulator is used and converted once.
 MAX_BF16_ACCUM_BLOCKS = 4
 
@@ -328,7 +331,7 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     if compact_ignored and kind == KIND_CE:
         idx, cnt = compact_rows(labels)
         n_valid = int(cnt.item())                     # the one host synchronisation of this mode
-        if 0 < n_valid < n:
+        if 0 < n_valid <= COMPACT_MAX_FRACTION * n:
             sub_reduction, sub_coef = reduction, coef
             if reduction == "seq_mean":               # per-sequence sums are rebuilt from the scattered row terms below
                 if not n_seqs or n % n_seqs:
