@@ -185,3 +185,21 @@ def test_head_loss_operator_is_registered_with_a_fake_kernel():
     with pytest.raises(RuntimeError, match="CUDA"):
         op(torch.zeros(8, 16, dtype=torch.bfloat16), torch.zeros(32, 16, dtype=torch.bfloat16), 0, torch.zeros(8, dtype=torch.int64),
            None, None, None, None, 1.0, 1.0, "reference", 0, 0, True, True, False)
+
+
+def test_enable_fused_head_allreduce_without_a_process_group_is_a_no_op():
+    """Single process (no torch.distributed group): nothing to reduce, nothing is touched."""
+    from multimodal_unlearning_b200 import head, trainer as T
+    model = torch.nn.Sequential(torch.nn.Linear(8, 8))
+    assert T.enable_fused_head_allreduce(model) is None
+    assert head._DW_REDUCER is None
+    assert not getattr(model, "_ddp_params_and_buffers_to_ignore", [])
+
+
+def test_compaction_threshold_and_defaults():
+    from multimodal_unlearning_b200 import head
+    assert 0.5 < head.COMPACT_MAX_FRACTION < 1.0
+    assert head.DEFAULT_BLOCK_ROWS == 8192 and head.MAX_BF16_ACCUM_BLOCKS >= 1
+    # the operator schema carries the flag (bool, last argument)
+    schema = str(torch.ops.clear_b200.head_loss.default._schema)
+    assert "bool compact_ignored" in schema and "str reduction" in schema
