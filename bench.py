@@ -400,7 +400,7 @@ def main():
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 1.63e9, "traffic_note": "dram bytes read+written per launch, mean of the 4 contraction launches of a step (projection 1.14, teacher projection 1.17, dH 2.48, dW 1.75 GB), ncu --set full at 8192-row blocks (profiles/r01_head_ncu_summary.md); algorithmic operand+result bytes per launch 0.855 GB",
+                         "traffic": 1.65e9, "traffic_note": "dram bytes read+written per launch, mean of the 4 contraction launches of a step (projection 1.16, teacher projection 1.18, dH 2.51, dW 1.77 GB), ncu --set full at 8192-row blocks (profiles/r01_head_ncu_summary.md); algorithmic operand+result bytes per launch 0.855 GB",
                          "kernel": "gemm_bf16_kernel (tcgen05, cta_group::2)",
                          "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
                          "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
