@@ -331,6 +331,10 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
     float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(z)[v], x);
     if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    if (v + 3 * kThreads < nfull) {  // later vectors of the row on their way into L2 (kThreads = 512: 1536 vectors ahead)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(z) + v + 3 * kThreads));
+      if constexpr (kNeedsRef) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(zr) + v + 3 * kThreads));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float p, aux;
