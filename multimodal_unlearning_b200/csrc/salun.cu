@@ -47,24 +47,46 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// torch's bf16 add on a packed pair: operands widened to fp32, added, rounded to nearest-even bf16
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t g) {
+  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a));
+  const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g));
+  const __nv_bfloat162 r = __floats2bfloat162_rn(__fadd_rn(x.x, y.x), __fadd_rn(x.y, y.y));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// kWide: 256-bit accesses (sm_100 LDG/STG.E.ENL2.256; both pointers 32-byte aligned), else 128-bit
+template <bool kWide>
 __global__ void __launch_bounds__(256) accumulate_kernel(__nv_bfloat16* acc, const __nv_bfloat16* grad, int64_t n) {
-  const int64_t nvec = n >> 3;
+  constexpr int kElems = kWide ? 16 : 8;
+  const int64_t nvec = n / kElems;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    uint4 a = reinterpret_cast<const uint4*>(acc)[v];
-    const uint4 g = ld_stream(reinterpret_cast<const uint4*>(grad) + v);
-    __nv_bfloat162* ah = reinterpret_cast<__nv_bfloat162*>(&a);
-    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g);
+    if constexpr (kWide) {
+      uint32_t a[8], g[8];
+      asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+                   : "l"(acc + v * 16));
+      asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]), "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7])
+                   : "l"(grad + v * 16));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      // torch's bf16 add: operands widened to fp32, added, rounded to nearest-even bf16
-      const float2 x = __bfloat1622float2(ah[j]), y = __bfloat1622float2(gh[j]);
-      ah[j] = __floats2bfloat162_rn(__fadd_rn(x.x, y.x), __fadd_rn(x.y, y.y));
+      for (int j = 0; j < 8; ++j) a[j] = add_bf16x2(a[j], g[j]);
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(acc + v * 16), "r"(a[0]), "r"(a[1]), "r"(a[2]),
+                   "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
+                   : "memory");
+    } else {
+      uint4 a = reinterpret_cast<const uint4*>(acc)[v];
+      const uint4 g = ld_stream(reinterpret_cast<const uint4*>(grad) + v);
+      a.x = add_bf16x2(a.x, g.x);
+      a.y = add_bf16x2(a.y, g.y);
+      a.z = add_bf16x2(a.z, g.z);
+      a.w = add_bf16x2(a.w, g.w);
+      reinterpret_cast<uint4*>(acc)[v] = a;
     }
-    reinterpret_cast<uint4*>(acc)[v] = a;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int64_t i = nvec << 3; i < n; ++i)
+    for (int64_t i = nvec * kElems; i < n; ++i)
       acc[i] = __float2bfloat16_rn(__fadd_rn(__bfloat162float(acc[i]), __bfloat162float(grad[i])));
   }
 }
@@ -715,8 +737,12 @@ int clear_saliency_accumulate(void* acc, const void* grad, int64_t n, void* stre
   if (n <= 0) return fail(CLEAR_ERR_SHAPE, "clear_saliency_accumulate: n <= 0");
   if ((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(grad)) & 15)
     return fail(CLEAR_ERR_ALIGN, "clear_saliency_accumulate: pointers must be 16-byte aligned");
-  accumulate_kernel<<<stream_grid(n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(acc), static_cast<const __nv_bfloat16*>(grad), n);
+  if (((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(grad)) & 31) == 0)
+    accumulate_kernel<true><<<stream_grid(n >> 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__nv_bfloat16*>(acc), static_cast<const __nv_bfloat16*>(grad), n);
+  else
+    accumulate_kernel<false><<<stream_grid(n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__nv_bfloat16*>(acc), static_cast<const __nv_bfloat16*>(grad), n);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }
