@@ -407,7 +407,8 @@ def main():
                          "frac_of_burst_peak": achieved / peaks["tflops_burst"],
                          "step_frac": flops_step / (ms / args.steps * 1e-3) / 1e12 / peak,
                          "rowloss_ms_per_step": rowloss_ms,
-                         "kernel_ms_per_step_fastest_rank": gemm_ms_fastest_rank},
+                         "kernel_ms_per_step_fastest_rank": gemm_ms_fastest_rank,
+                         "stages_ms_per_step": {k: [v[0] // args.steps, v[1] / args.steps] for k, v in sorted(summ.items())}},
             "cpu_baseline": cpu_base,
             "salun_hbm_roofline": salun_res,
             "clocks": clocks,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CLEAR_ABI_VERSION 2
+#define CLEAR_ABI_VERSION 3
 
 typedef enum ClearStatus {
   CLEAR_OK = 0,
@@ -102,12 +102,19 @@ typedef struct ClearProjectArgs {
   int64_t n_rows;
   int32_t hidden_dim, vocab;
   int32_t cta_group;
+  /* optional device-side row count (row compaction without a host round trip): only the first
+   * clamp(*n_rows_dev - n_rows_dev_offset, 0, n_rows) rows are projected; n_rows stays the allocation / upper bound */
+  const int32_t* n_rows_dev;
+  int32_t n_rows_dev_offset;
 } ClearProjectArgs;
 int clear_head_project(const ClearProjectArgs* args, void* stream);
 /* Same statistics for teacher logits handed over already materialised (`self.teacher_model(**x).logits`,
  * mm/trainer.py:199-200): lse_part float2 [n_rows][clear_head_vtiles(vocab)] from bf16 logits. */
 int clear_head_lse_partials(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
                             void* stream);
+/* the same for fp32 teacher logits (a teacher evaluated under autocast, or an fp32 oracle model) */
+int clear_head_lse_partials_f32(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
+                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Loss head, stage 2 — row-wise loss and d(loss)/d(logits), written in place over the logits.
@@ -135,6 +142,11 @@ typedef struct ClearRowLossArgs {
   float grad_scale;
   float beta;               /* NPO exponent (loss_beta) */
   int32_t write_grad;       /* 0: forward only (logits left untouched) */
+  int32_t ref_logits_f32;   /* ref_logits is fp32 [n_rows, ref_ld] instead of bf16 */
+  const int32_t* n_rows_dev; /* CE only: device-side row count (see ClearProjectArgs); the dlogits rows between the count and the */
+  int32_t n_rows_dev_offset; /* next multiple of 64 are zeroed (they fall into the last K block of the dW contraction)        */
+  int32_t* status_flags;    /* optional device int32: bit 0 is set when a CE label lies outside [0, vocab) (torch asserts there;
+                               the row's loss term is NaN, its dlogits zero) */
 } ClearRowLossArgs;
 int clear_head_rowloss(const ClearRowLossArgs* args, void* stream);
 
@@ -152,6 +164,16 @@ int clear_rows_gather(const void* src, int64_t src_ld_bytes, const int32_t* row_
                       void* dst, int64_t dst_ld_bytes, void* stream);
 int clear_rows_scatter(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx, int32_t row_bytes,
                        void* dst, int64_t dst_ld_bytes, void* stream);
+/* The same with the number of indices read from device memory (*n_idx_dev <= n_idx_max; NULL = n_idx_max), so that the
+ * count of clear_head_compact_rows never visits the host.  Gather: row_index NULL = identity, and with pad_to > 0 the
+ * destination rows [n, round_up(n, pad_to)) below n_idx_max are zero-filled.
+ * clear_index_compose: out[i] = outer[inner[i]], i < n — valid rows of a batch whose rows are themselves a row map
+ * (remove_image_tokens, mm/trainer_utils.py:48-70) of the trunk's output. */
+int clear_rows_gather_dev(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx_max,
+                          const int32_t* n_idx_dev, int32_t pad_to, int32_t row_bytes, void* dst, int64_t dst_ld_bytes, void* stream);
+int clear_rows_scatter_dev(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx_max,
+                           const int32_t* n_idx_dev, int32_t row_bytes, void* dst, int64_t dst_ld_bytes, void* stream);
+int clear_index_compose(const int32_t* inner, const int32_t* outer, int64_t n_max, const int32_t* n_dev, int32_t* out, void* stream);
 /* out[0] (+)= scale * (scale_dev ? *scale_dev : 1) * sum_i loss_rows[i]   — deterministic single-block tree */
 int clear_head_reduce_rows(const float* loss_rows, int64_t n_rows, float scale, const float* scale_dev,
                            float* out, int accumulate, void* stream);
@@ -187,6 +209,11 @@ typedef struct ClearBackwardArgs {
    * the all-reduce. */
   void* dweight_peers[8];
   int32_t n_peers;
+  /* optional device-side row count (see ClearProjectArgs): dH is formed for the live rows only (with dhidden_ws the K split
+   * that fills the SMs is chosen inside the kernel); dW contracts over round_up(count, 64) rows — dlogits and hidden must be
+   * zero between the count and that bound (clear_head_rowloss / clear_rows_gather_dev see to it). */
+  const int32_t* n_rows_dev;
+  int32_t n_rows_dev_offset;
 } ClearBackwardArgs;
 int clear_head_backward(const ClearBackwardArgs* args, void* stream);
 /* Rows [row0, row1) of dW that `rank` owns among n_peers (contiguous slabs of whole output tiles). */
@@ -241,6 +268,22 @@ typedef struct ClearHeadArgs {
   int32_t block_rows;      /* rows staged per pass; 0 = 8192 */
   int32_t dweight_f32, dweight_accumulate;
   int32_t cta_group;
+  /* ---- ABI 3 ---- */
+  /* Row map (remove_image_tokens, mm/trainer_utils.py:48-70, as a kernel input instead of a copy of [B, L, V] logits): row i
+   * of this invocation is row row_index[i] of hidden / ref_hidden, which then hold n_src_rows rows; its gradient goes to that
+   * row of dhidden [n_src_rows, dhidden_ld], whose other rows are zero-filled.  labels, ref_logits, row_weight, loss_rows and
+   * the sequences of seq_loss are indexed by i.  NULL = identity. */
+  const int32_t* row_index;
+  int64_t n_src_rows;
+  /* CE only: evaluate the rows whose label is not -100 only (they alone contribute to the loss, to dW and to their own dH):
+   * valid rows are compacted on the device and their count never visits the host — every stage reads it from device memory.
+   * Same loss, loss_rows, dhidden, dweight as the full evaluation (dW up to the summation order of the bf16 products). */
+  int32_t compact_ignored;
+  int32_t ref_logits_f32;  /* ref_logits is fp32 instead of bf16 */
+  int32_t* status_flags;   /* optional device int32, OR-ed: bit 0 = a CE label outside [0, vocab) (torch raises a device assert) */
+  /* optional cudaEvent_t: the stream waits on it (cudaStreamWaitEvent) right before the first launch that writes into
+   * dweight_peers — the owners have zeroed their slabs — instead of the caller holding the whole invocation back */
+  void* dweight_ready_event;
 } ClearHeadArgs;
 int clear_head_loss_workspace_bytes(const ClearHeadArgs* args, size_t* out_bytes);
 int clear_head_loss_fwd_bwd(const ClearHeadArgs* args, void* workspace, size_t workspace_bytes, void* stream);
@@ -275,6 +318,22 @@ int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, 
  * n_chunks = chunk_prefix[n_segs]; tie_scratch: uint64 [n_chunks] workspace.
  * One streaming pass writes the mask speculating on the tie boundary from the histogram; a scan of the
  * chunk tie counts and an audit pass rewrite the few chunks that guessed wrong (result is exact). */
+/* Global-threshold scope (upstream SalUn's global rank, of which the reference's `start_index` at generate_mask.py:59,83 is
+ * the vestige): ONE ranking over all tensors, k = (int64)(th * n_total), ties by global flat index.
+ *   clear_saliency_hist_total         total[bin] = sum over tensors of hist (zero padding excluded); int64 [32768].  With the
+ *                                     flat buffer sharded over ranks the caller all-reduces `total` (256 KB) at this point.
+ *   clear_saliency_select_global_tau  tau_budget int64 [n_th][2] = (threshold key or -1 when k == 0, tie budget).
+ *   clear_saliency_select_global_fill the per-tensor records clear_saliency_select writes, for the common key: tensor s takes
+ *                                     clamp(budget - #ties in earlier tensors, 0, #ties in s) ties; budget_override (device
+ *                                     int64 [n_th], optional) replaces the budget — this rank's share of it.
+ * The mask entry points consume the records unchanged. */
+int clear_saliency_hist_total(const uint32_t* hist, const int64_t* seg_offsets_dev, const int64_t* seg_numel_dev, int32_t n_segs,
+                              int64_t* total, void* stream);
+int clear_saliency_select_global_tau(const int64_t* total, int64_t n_total, const double* thresholds_host, int32_t n_th,
+                                     int64_t* tau_budget, void* stream);
+int clear_saliency_select_global_fill(const uint32_t* hist, const int64_t* seg_offsets_dev, const int64_t* seg_numel_dev,
+                                      int32_t n_segs, const int64_t* tau_budget, const int64_t* budget_override, int32_t n_th,
+                                      int64_t* select, void* stream);
 int64_t clear_saliency_chunk_elems(void);
 int clear_saliency_mask(const void* acc, const int64_t* seg_offsets_dev, const int64_t* chunk_prefix_dev,
                         int32_t n_segs, int64_t n_chunks, const int64_t* select, int32_t n_th, int32_t th_index,

@@ -23,7 +23,11 @@ EXPORTED_SYMBOLS = (
     "clear_param_l1_grad", "clear_grad_scale", "clear_saliency_mask_bits", "clear_mask_pack", "clear_mask_unpack",
     "clear_head_dweight_slab", "clear_dweight_allgather", "clear_head_compact_rows", "clear_rows_gather", "clear_rows_scatter",
     "clear_head_loss_workspace_bytes", "clear_head_loss_fwd_bwd",
+    # ABI 3
+    "clear_head_lse_partials_f32", "clear_rows_gather_dev", "clear_rows_scatter_dev", "clear_index_compose",
+    "clear_saliency_hist_total", "clear_saliency_select_global_tau", "clear_saliency_select_global_fill",
 )
+ABI_VERSION = 3
 
 
 class GemmArgs(C.Structure):
@@ -38,7 +42,8 @@ class GemmArgs(C.Structure):
 class ProjectArgs(C.Structure):
     _fields_ = [("hidden", C.c_void_p), ("weight", C.c_void_p), ("logits", C.c_void_p), ("lse_part", C.c_void_p),
                 ("hidden_ld", C.c_int64), ("weight_ld", C.c_int64), ("logits_ld", C.c_int64),
-                ("n_rows", C.c_int64), ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("cta_group", C.c_int32)]
+                ("n_rows", C.c_int64), ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("cta_group", C.c_int32),
+                ("n_rows_dev", C.c_void_p), ("n_rows_dev_offset", C.c_int32)]
 
 
 class RowLossArgs(C.Structure):
@@ -47,7 +52,8 @@ class RowLossArgs(C.Structure):
                 ("scale_dev", C.c_void_p), ("loss_rows", C.c_void_p),
                 ("logits_ld", C.c_int64), ("ref_ld", C.c_int64), ("n_rows", C.c_int64),
                 ("vocab", C.c_int32), ("kind", C.c_int32), ("grad_scale", C.c_float), ("beta", C.c_float),
-                ("write_grad", C.c_int32)]
+                ("write_grad", C.c_int32), ("ref_logits_f32", C.c_int32), ("n_rows_dev", C.c_void_p),
+                ("n_rows_dev_offset", C.c_int32), ("status_flags", C.c_void_p)]
 
 
 class BackwardArgs(C.Structure):
@@ -57,7 +63,8 @@ class BackwardArgs(C.Structure):
                 ("dhidden_ld", C.c_int64), ("dweight_ld", C.c_int64), ("n_rows", C.c_int64),
                 ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("dweight_f32", C.c_int32),
                 ("accumulate", C.c_int32), ("cta_group", C.c_int32), ("dhidden_ws", C.c_void_p),
-                ("dweight_peers", C.c_void_p * 8), ("n_peers", C.c_int32)]
+                ("dweight_peers", C.c_void_p * 8), ("n_peers", C.c_int32),
+                ("n_rows_dev", C.c_void_p), ("n_rows_dev_offset", C.c_int32)]
 
 
 REDUCE_REFERENCE, REDUCE_SUM, REDUCE_SEQ_MEAN = 0, 1, 2
@@ -72,7 +79,9 @@ class HeadArgs(C.Structure):
                 ("ref_logits_ld", C.c_int64), ("dhidden_ld", C.c_int64), ("dweight_ld", C.c_int64), ("n_rows", C.c_int64),
                 ("hidden_dim", C.c_int32), ("vocab", C.c_int32), ("kind", C.c_int32), ("beta", C.c_double), ("coef", C.c_double),
                 ("reduction", C.c_int32), ("n_seqs", C.c_int32), ("block_rows", C.c_int32), ("dweight_f32", C.c_int32),
-                ("dweight_accumulate", C.c_int32), ("cta_group", C.c_int32)]
+                ("dweight_accumulate", C.c_int32), ("cta_group", C.c_int32),
+                ("row_index", C.c_void_p), ("n_src_rows", C.c_int64), ("compact_ignored", C.c_int32),
+                ("ref_logits_f32", C.c_int32), ("status_flags", C.c_void_p), ("dweight_ready_event", C.c_void_p)]
 
 
 class AdamWArgs(C.Structure):
@@ -133,12 +142,22 @@ def load() -> C.CDLL:
     lib.clear_head_compact_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.clear_rows_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     lib.clear_rows_scatter.argtypes = lib.clear_rows_gather.argtypes
+    lib.clear_head_lse_partials_f32.argtypes = lib.clear_head_lse_partials.argtypes
+    lib.clear_rows_gather_dev.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_int64, C.c_void_p]
+    lib.clear_rows_scatter_dev.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                           C.c_void_p]
+    lib.clear_index_compose.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.clear_saliency_hist_total.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.clear_saliency_select_global_tau.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p]
+    lib.clear_saliency_select_global_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                      C.c_void_p, C.c_void_p]
     lib.clear_head_loss_workspace_bytes.argtypes = [C.POINTER(HeadArgs), C.POINTER(C.c_size_t)]
     lib.clear_head_loss_fwd_bwd.argtypes = [C.POINTER(HeadArgs), C.c_void_p, C.c_size_t, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError here = the .so is stale / does not match include/clear_b200.h
-    if lib.clear_abi_version() != 2:
-        raise RuntimeError(f"libclear_b200.so ABI version {lib.clear_abi_version()} != 2; rebuild the library")
+    if lib.clear_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libclear_b200.so ABI version {lib.clear_abi_version()} != {ABI_VERSION}; rebuild the library")
     _lib = lib
     return lib
 

@@ -37,9 +37,19 @@ struct GemmOperand {
 };
 // peer_d / n_peers: optional output buffers of the data-parallel peers (same shape and ldd as d; d itself may be one of
 // them): M tiles are reduce-added into the buffer of their owner rank (see PeerMaps in gemm_sm100.cuh).
+// dyn: optional device-side extent.  *count - offset (clamped) replaces m (dim = 1) or k (dim = 2, rounded up to a multiple of
+// 64; the operand rows of the last K block beyond the count must be zero); m / k are then upper bounds.  splits = 1 (dim = 1,
+// fp32 reduce-add output, pre-zeroed): the number of K splits is chosen in the kernel from the actual m.
+struct GemmDyn {
+  const int* count = nullptr;
+  int offset = 0;
+  int dim = 0;
+  int splits = 0;
+};
 int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
                      int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits = 1,
-                     void* const* peer_d = nullptr, int n_peers = 0);
+                     void* const* peer_d = nullptr, int n_peers = 0, GemmDyn dyn = GemmDyn());
+int current_device();   // ordinal of the current device, < 0 on error (per-device caches)
 // Rows [row0, row1) of an [m, *] output that rank `rank` of `n_peers` owns under that sharding.
 void gemm_peer_rows(int cta_group, int m, int n_peers, int rank, int* row0, int* row1);
 // Number of K splits (1..4) that best fills the last wave of CTA groups for this problem.

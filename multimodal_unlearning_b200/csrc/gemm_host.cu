@@ -2,6 +2,7 @@
 // runtime, so libcuda is never linked), kernel-variant dispatch, persistent-grid launch.
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.h"
@@ -26,13 +27,23 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 const char* last_error() { return g_err; }
 
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
+// cached per device ordinal: one process may drive several GPUs (device_map="auto" teachers, multi-GPU tests)
 int device_sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  static std::atomic<int> cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0) return -1;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  cached = n;
+  cached[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 
@@ -97,7 +108,6 @@ static int make_output_map(CUtensorMap* tm, void* d, int d_is_f32, int64_t ldd, 
 // device allocation.  A kernel's last CTA group re-arms its pair, so consecutive launches need no memset between them.
 static int next_work_counter(unsigned int** out) {
   constexpr int kRing = 4096;
-  constexpr int kMaxDevices = 64;
   static unsigned int* ring[kMaxDevices] = {};
   static unsigned int cursor[kMaxDevices] = {};
   static std::mutex mu;
@@ -120,16 +130,20 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           const GemmParams& p, cudaStream_t stream) {
   using S = GemmShape<kCtaGroup>;
   auto kern = gemm_bf16_kernel<kCtaGroup, kMajorA, kMajorB, kEpi>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
+  static std::atomic<bool> configured[kMaxDevices] = {};  // per template instantiation and device (the attribute is per device)
+  const int dev = current_device();
+  if (dev < 0) return fail(CLEAR_ERR_DEVICE, "cannot query the current device");
+  if (!configured[dev].load(std::memory_order_acquire)) {
     CLEAR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
-    configured = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   const int sms = device_sm_count();
   if (sms <= 0) return fail(CLEAR_ERR_DEVICE, "cannot query SM count");
-  const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int tiles = p.m_tiles * p.n_tiles * (p.dyn_splits ? 4 : p.k_splits);
   int groups = sms / kCtaGroup;
   if (groups > tiles) groups = tiles;
+  GemmParams pl = p;
+  pl.sm_groups = groups;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * kCtaGroup));
   cfg.blockDim = dim3(S::THREADS);
@@ -142,7 +156,7 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CLEAR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, peers, p));
+  CLEAR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, peers, pl));
   return 0;
 }
 
@@ -211,9 +225,20 @@ void gemm_peer_rows(int cta_group, int m, int n_peers, int rank, int* row0, int*
   *row1 = (int)r1;
 }
 
+// diagnostic tile-order override CLEAR_GEMM_RASTER="<m_fast>,<group>", read once
+static bool raster_override(int* m_fast, int* group) {
+  static const struct Ov { bool on; int mf, grp; } ov = [] {
+    Ov o{false, 0, 0};
+    if (const char* e = getenv("CLEAR_GEMM_RASTER")) o.on = (sscanf(e, "%d,%d", &o.mf, &o.grp) == 2 && o.grp > 0);
+    return o;
+  }();
+  if (ov.on) { *m_fast = ov.mf ? 1 : 0; *group = ov.grp; }
+  return ov.on;
+}
+
 int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
                      int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits,
-                     void* const* peer_d, int n_peers) {
+                     void* const* peer_d, int n_peers, GemmDyn dyn) {
   if (!a.ptr || !b.ptr || !d) return fail(CLEAR_ERR_NULL, "gemm: null operand");
   if (m <= 0 || n <= 0 || k <= 0) return fail(CLEAR_ERR_SHAPE, "gemm: non-positive dims m=%d n=%d k=%d", m, n, k);
   if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
@@ -262,10 +287,7 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
     p.raster_m_fast = raster_m_fast ? 1 : 0;
     p.raster_group = raster_m_fast ? p.m_tiles : p.n_tiles;  // whole-dimension chunks
   }
-  if (const char* e = getenv("CLEAR_GEMM_RASTER")) {  // diagnostic override: "<m_fast>,<group>"
-    int mf = 0, grp = 0;
-    if (sscanf(e, "%d,%d", &mf, &grp) == 2 && grp > 0) { p.raster_m_fast = mf ? 1 : 0; p.raster_group = grp; }
-  }
+  raster_override(&p.raster_m_fast, &p.raster_group);
   {
     const int fast = p.raster_m_fast ? p.m_tiles : p.n_tiles;
     if (p.raster_group > fast) p.raster_group = fast;
@@ -283,6 +305,14 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
   if ((rc = next_work_counter(&p.work_counter))) return rc;
   p.n_peers = n_peers;
   p.mtiles_per_peer = n_peers > 0 ? peer_mtiles(cta_group, m, n_peers) : 1;
+  p.dyn_count = dyn.count;
+  p.dyn_offset = dyn.offset;
+  p.dyn_dim = dyn.count ? dyn.dim : 0;
+  p.dyn_splits = (dyn.count && dyn.dim == 1) ? dyn.splits : 0;
+  p.sm_groups = 1;
+  if (p.dyn_dim != 0 && p.dyn_dim != 1 && p.dyn_dim != 2) return fail(CLEAR_ERR_KIND, "gemm: dyn.dim must be 1 (M) or 2 (K)");
+  if (p.dyn_dim == 2 && p.k_splits > 1) return fail(CLEAR_ERR_KIND, "gemm: a device-side K extent excludes split-K");
+  if (p.dyn_splits && !(reduce_add && d_is_f32)) return fail(CLEAR_ERR_KIND, "gemm: in-kernel split-K needs the fp32 reduce-add epilogue");
 
   const int epi = d_is_f32 ? kEpiStoreF32 : (lse_part ? kEpiStoreBF16Lse : kEpiStoreBF16);
 #define CLEAR_DISPATCH(CG, MA, MB, EPI)                                                     \

@@ -47,6 +47,15 @@ struct GemmParams {
                                // two launches on a stream
   int n_peers;                 // > 0: the output is sharded by M tiles over the peers' buffers (fused reduce-scatter)
   int mtiles_per_peer;         // owner of M tile mt = min(n_peers - 1, mt / mtiles_per_peer)
+  // Device-side extent (row compaction without a host round trip): *dyn_count - dyn_offset, clamped to [0, M or K], replaces
+  // M (dyn_dim = 1: projection / dH over the valid rows only) or K rounded up to a K block (dyn_dim = 2: dW; the operand
+  // rows of the last block beyond the count must be zero).  The tensor maps, the grid and the tile order are those of the
+  // host-side maximum.  dyn_dim = 1 with dyn_splits: the number of K splits is chosen in the kernel from the actual M.
+  const int* dyn_count;
+  int dyn_offset;
+  int dyn_dim;
+  int dyn_splits;              // 1: choose k_splits in-kernel (fp32 reduce-add epilogue, D pre-zeroed); 0: k_splits as given
+  int sm_groups;               // CTA groups of the launch (in-kernel split choice)
 };
 
 // Output tensor maps of the peers' buffers (symmetric memory mapped over NVLink / NVSwitch): with n_peers > 0 the epilogue
@@ -159,14 +168,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
+  // Device-side extents (see GemmParams::dyn_count): every thread derives the same values.
+  int dynM = p.M, dynK = p.K, m_tiles = p.m_tiles, k_splits = p.k_splits, kb_per_split = p.kb_per_split;
+  if (p.dyn_dim != 0) {
+    int c = *p.dyn_count - p.dyn_offset;
+    c = max(c, 0);
+    if (p.dyn_dim == 1) {
+      dynM = min(c, p.M);
+      m_tiles = (dynM + S::BM * kCtaGroup - 1) / (S::BM * kCtaGroup);
+      if (p.dyn_splits) {  // same rule as gemm_pick_k_splits (gemm_host.cu), on the actual number of output tiles
+        const int tiles = m_tiles * p.n_tiles, num_kb = (p.K + S::BK - 1) / S::BK;
+        int best = 1;
+        float best_eff = 0.f;
+        for (int sp = 1; sp <= 4 && tiles > 0; ++sp) {
+          if (sp > 1 && num_kb / sp < 64) break;
+          const float waves = (float)tiles * sp / (float)p.sm_groups;
+          const float eff = waves / ceilf(waves - 1e-6f);
+          if (eff > best_eff + 0.03f) { best_eff = eff; best = sp; }
+        }
+        kb_per_split = (num_kb + best - 1) / best;
+        k_splits = (num_kb + kb_per_split - 1) / kb_per_split;
+      }
+    } else {
+      dynK = min((c + S::BK - 1) / S::BK * S::BK, (p.K + S::BK - 1) / S::BK * S::BK);
+      kb_per_split = (dynK + S::BK - 1) / S::BK;  // dyn_dim = 2 excludes split-K
+      k_splits = 1;
+    }
+  }
   // Work item w = (output tile, K split): consecutive items are the splits of one tile.
-  const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
-  const int num_kb_total = (p.K + S::BK - 1) / S::BK;
+  const int num_tiles = m_tiles * p.n_tiles * k_splits;
+  const int num_kb_total = (dynK + S::BK - 1) / S::BK;   // 0 (no valid row at all): the epilogue emits zeros
 
   // Work item -> output tile.  Chunks of `raster_group` tiles along the fast dimension, each swept across the slow one.
   auto tile_coords = [&](int t, int& mt, int& nt) {
-    const int fast_tiles = p.raster_m_fast ? p.m_tiles : p.n_tiles;
-    const int slow_tiles = p.raster_m_fast ? p.n_tiles : p.m_tiles;
+    const int fast_tiles = p.raster_m_fast ? m_tiles : p.n_tiles;
+    const int slow_tiles = p.raster_m_fast ? p.n_tiles : m_tiles;
     const int per_chunk = p.raster_group * slow_tiles;
     const int c = t / per_chunk;
     const int r = t - c * per_chunk;
@@ -219,9 +255,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       while (w < num_tiles) {
         unsigned int next_claim = 0;
         if (leader) next_claim = atomicAdd(p.work_counter, 1u);
-        const int t = w / p.k_splits;
-        const int kb0 = (w % p.k_splits) * p.kb_per_split;
-        const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        const int t = w / k_splits;
+        const int kb0 = (w % k_splits) * kb_per_split;
+        const int kb1 = min(num_kb_total, kb0 + kb_per_split);
         int mt, nt;
         tile_coords(t, mt, nt);
         const int m0 = (mt * kCtaGroup + (int)cta_rank) * S::BM;
@@ -270,8 +306,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t b_lbo = (kMajorB == kMajorK) ? 16u : (S::BK * 128);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
       for (int w = sched_read(slot, sphase); w < num_tiles; w = sched_read(slot, sphase)) {
-        const int kb0 = (w % p.k_splits) * p.kb_per_split;
-        const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        const int kb0 = (w % k_splits) * kb_per_split;
+        const int kb1 = min(num_kb_total, kb0 + kb_per_split);
         ptx::mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * S::BN;
@@ -306,7 +342,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) w = sched_read(slot, sphase);
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w >= num_tiles) break;
-      const int t = w / p.k_splits;
+      const int t = w / k_splits;
       int mt, nt;
       tile_coords(t, mt, nt);
       const int row0 = (mt * kCtaGroup + (int)cta_rank) * S::BM + (int)q * 32;
@@ -328,13 +364,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
           ptx::tmem_ld_wait();
+          if (num_kb_total == 0) {  // no MMA ran: the accumulator is not defined
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
           const uint32_t rowp = buf + lane * 128u;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             ptx::st_shared_v4(rowp + (((uint32_t)j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && col0 + c * 32 < p.N) {
+          if (lane == 0 && row0 < dynM && col0 + c * 32 < p.N) {
             if (reduce_out) ptx::tma_reduce_add_2d(tmOut, buf, col0 + c * 32, row0);
             else            ptx::tma_store_2d(tmOut, buf, col0 + c * 32, row0);
           }
@@ -353,6 +393,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
           ptx::tmem_ld_wait();
+          if (num_kb_total == 0) {  // no MMA ran: the accumulator is not defined
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v0[j] = 0u; v1[j] = 0u; }
+          }
           uint32_t pk[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -388,7 +432,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::st_shared_v4(rowp + (((uint32_t)j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && col0 + c * 64 < p.N) {
+          if (lane == 0 && row0 < dynM && col0 + c * 64 < p.N) {
             if (reduce_out) ptx::tma_reduce_add_2d(tmOut, buf, col0 + c * 64, row0);  // bf16 += (rounded in L2)
             else            ptx::tma_store_2d(tmOut, buf, col0 + c * 64, row0);
           }
@@ -397,7 +441,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if constexpr (kEpi == kEpiStoreBF16Lse) {
           const int row = row0 + (int)lane;
-          if (row < p.M) p.lse_part[(size_t)row * p.n_tiles + nt] = make_float2(run_max, run_sum);
+          if (row < dynM) p.lse_part[(size_t)row * p.n_tiles + nt] = make_float2(run_max, run_sum);
         }
       }
       // every tcgen05.ld of this accumulator stage has completed (wait::ld above): hand it back

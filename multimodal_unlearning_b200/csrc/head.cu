@@ -8,6 +8,8 @@
 // the backward projections consume that buffer.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.h"
 #include "gemm_sm100.cuh"
 
@@ -27,7 +29,7 @@ constexpr int kRowL2Ahead = 6;
 struct RowLossParams {
   __nv_bfloat16* logits;
   const float2* lse_part;
-  const __nv_bfloat16* ref_logits;
+  const void* ref_logits;  // bf16 or fp32 (template parameter kRefF32 of the kernels)
   const float2* ref_lse_part;
   const int64_t* labels;
   const float* row_weight;
@@ -37,7 +39,40 @@ struct RowLossParams {
   int vocab, n_vtiles;
   float grad_scale, beta;
   int write_grad;
+  const int* m_dev;   // optional device-side row count (row compaction): rows >= *m_dev - m_off are not evaluated; those below the
+  int m_off;          // next multiple of 64 get zero dlogits (they fall into the last K block of the dW contraction)
+  int* status_flags;  // optional: bit 0 <- a CE label outside [0, vocab)
 };
+
+// Teacher logits arrive as bf16 (a bf16 checkpoint's lm_head output: the reference's case, SURVEY.md App. A dtype notes) or as
+// fp32 (a teacher evaluated under autocast / an fp32 oracle).  One 8-logit vector = 16 or 32 bytes.
+template <bool kF32>
+struct RefVec {
+  uint4 a, b;
+};
+template <bool kF32>
+__device__ __forceinline__ RefVec<kF32> ld_ref8(const void* row, int v) {
+  RefVec<kF32> r;
+  if constexpr (kF32) {
+    r.a = reinterpret_cast<const uint4*>(row)[2 * v];
+    r.b = reinterpret_cast<const uint4*>(row)[2 * v + 1];
+  } else {
+    r.a = reinterpret_cast<const uint4*>(row)[v];
+    r.b = r.a;
+  }
+  return r;
+}
+template <bool kF32>
+__device__ __forceinline__ RefVec<kF32> zero_ref8() {
+  RefVec<kF32> r;
+  r.a = make_uint4(0, 0, 0, 0);
+  r.b = r.a;
+  return r;
+}
+template <bool kF32>
+__device__ __forceinline__ void prefetch_ref8(const void* row, int v) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char*>(row) + (size_t)v * (kF32 ? 32 : 16)));
+}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -116,6 +151,15 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float (&x)[8]) {
     x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
   }
 }
+template <bool kF32>
+__device__ __forceinline__ void unpack_ref8(const RefVec<kF32>& raw, float (&x)[8]) {
+  if constexpr (kF32) {
+    x[0] = __uint_as_float(raw.a.x); x[1] = __uint_as_float(raw.a.y); x[2] = __uint_as_float(raw.a.z); x[3] = __uint_as_float(raw.a.w);
+    x[4] = __uint_as_float(raw.b.x); x[5] = __uint_as_float(raw.b.y); x[6] = __uint_as_float(raw.b.z); x[7] = __uint_as_float(raw.b.w);
+  } else {
+    unpack8(raw.a, x);
+  }
+}
 __device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
   uint4 raw;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
@@ -144,10 +188,27 @@ template <int kThreads>
 __global__ void __launch_bounds__(kThreads) rowloss_ce_kernel(const RowLossParams a) {
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
+  if (a.m_dev) {  // row compaction: only the first *m_dev - m_off rows of this block exist
+    const int m = *a.m_dev - a.m_off;
+    if (row >= m) {
+      if (a.write_grad && row < ((max(m, 0) + 63) & ~63)) {
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        for (int v = threadIdx.x; v < (int)(a.ld >> 3); v += kThreads) reinterpret_cast<uint4*>(z)[v] = zero;
+      }
+      return;
+    }
+  }
   const int64_t y = a.labels[row];
   const bool valid = (y != kIgnoreIndex);
-  if (valid && (y < 0 || y >= a.vocab)) {  // torch raises a device-side assert here; be as loud as a kernel can
-    if (threadIdx.x == 0) a.loss_rows[row] = __int_as_float(0x7fc00000);
+  if (valid && (y < 0 || y >= a.vocab)) {  // torch raises a device-side assert here; be as loud as a kernel can:
+    if (threadIdx.x == 0) {                // NaN loss row (poisons the loss) and the caller's status flag
+      a.loss_rows[row] = __int_as_float(0x7fc00000);
+      if (a.status_flags) atomicOr(a.status_flags, 1);
+    }
+    if (a.write_grad) {
+      const uint4 zero = make_uint4(0, 0, 0, 0);
+      for (int v = threadIdx.x; v < (int)(a.ld >> 3); v += kThreads) reinterpret_cast<uint4*>(z)[v] = zero;
+    }
     return;
   }
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
@@ -196,18 +257,19 @@ __global__ void __launch_bounds__(kThreads) rowloss_ce_kernel(const RowLossParam
 // ---------------------------------------------------------------------------------------------------
 // forward KL: loss_row = sum q (lq - lp); dz = g (p - q).  Streaming, one pass.  (A4)
 // ---------------------------------------------------------------------------------------------------
-template <int kThreads>
+template <int kThreads, bool kRefF32>
 __global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossParams a) {
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
-  const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
+  const char* zr = static_cast<const char*>(a.ref_logits) + row * a.ref_ld * (kRefF32 ? 4 : 2);
   const int nvec = (int)(a.ld >> 3);
   const int nfull = a.vocab >> 3;
   const int ref_nvec = (int)(a.ref_ld >> 3);  // a materialised teacher may be narrower than the staging buffer
-  auto ld_ref = [&](int v) { return v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0); };
+  auto ld_ref = [&](int v) { return v < ref_nvec ? ld_ref8<kRefF32>(zr, v) : zero_ref8<kRefF32>(); };
   // first vector pair in flight while the row statistics are merged; register double-buffering afterwards
-  uint4 nx = make_uint4(0, 0, 0, 0), nr = nx;
+  uint4 nx = make_uint4(0, 0, 0, 0);
+  RefVec<kRefF32> nr = zero_ref8<kRefF32>();
   if ((int)threadIdx.x < nvec) {
     nx = reinterpret_cast<const uint4*>(z)[threadIdx.x];
     nr = ld_ref(threadIdx.x);
@@ -221,14 +283,14 @@ __global__ void __launch_bounds__(kThreads) rowloss_klfwd_kernel(const RowLossPa
   for (int v = threadIdx.x; v < nvec; v += kThreads) {
     float x[8], r[8];
     unpack8(nx, x);
-    unpack8(nr, r);
+    unpack_ref8<kRefF32>(nr, r);
     if (v + kThreads < nvec) {
       nx = reinterpret_cast<const uint4*>(z)[v + kThreads];
       nr = ld_ref(v + kThreads);
     }
     if (v + kRowL2Ahead * kThreads < min(nvec, ref_nvec)) {
       asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(z) + v + kRowL2Ahead * kThreads));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(zr) + v + kRowL2Ahead * kThreads));
+      prefetch_ref8<kRefF32>(zr, v + kRowL2Ahead * kThreads);
     }
     if (v < nfull) {
 #pragma unroll
@@ -306,13 +368,13 @@ struct RowTerm {
   }
 };
 
-template <int kKind, bool kBetaOne, int kThreads>
+template <int kKind, bool kBetaOne, int kThreads, bool kRefF32>
 __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLossParams a) {
   __shared__ float red[32];
   constexpr bool kNeedsRef = (kKind != CLEAR_KIND_ENTROPY);
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
-  const __nv_bfloat16* zr = kNeedsRef ? a.ref_logits + row * a.ref_ld : nullptr;
+  const char* zr = kNeedsRef ? static_cast<const char*>(a.ref_logits) + row * a.ref_ld * (kRefF32 ? 4 : 2) : nullptr;
   RowConsts c;
   float lse_t = 0.f;
   if constexpr (kNeedsRef) merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, c.lse_s, lse_t);
@@ -330,10 +392,10 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
   for (int v = threadIdx.x; v < nfull; v += kThreads) {
     float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-    if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+    if constexpr (kNeedsRef) unpack_ref8<kRefF32>(ld_ref8<kRefF32>(zr, v), r);
     if (v + 3 * kThreads < nfull) {  // later vectors of the row on their way into L2 (kThreads = 512: 1536 vectors ahead)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(z) + v + 3 * kThreads));
-      if constexpr (kNeedsRef) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(zr) + v + 3 * kThreads));
+      if constexpr (kNeedsRef) prefetch_ref8<kRefF32>(zr, v + 3 * kThreads);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -346,7 +408,7 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
     if (threadIdx.x == 0 && (a.vocab & 7)) {
       float x[8], r[8];
       unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-      if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
+      if constexpr (kNeedsRef) unpack_ref8<kRefF32>(v < ref_nvec ? ld_ref8<kRefF32>(zr, v) : zero_ref8<kRefF32>(), r);
       for (int j = 0; j < (a.vocab & 7); ++j) {
         float p, aux;
         RowTerm<kKind, kBetaOne>::eval(x[j], kNeedsRef ? r[j] : 0.f, c, p, aux, stat, loss);
@@ -363,7 +425,7 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
     float x[8], r[8];
     if (v < nfull) {
       unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-      if constexpr (kNeedsRef) unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+      if constexpr (kNeedsRef) unpack_ref8<kRefF32>(ld_ref8<kRefF32>(zr, v), r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float p, aux, st = 0.f, ls = 0.f;
@@ -372,7 +434,7 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
       }
     } else {  // ragged / padding vectors
       unpack8(reinterpret_cast<const uint4*>(z)[v], x);
-      if constexpr (kNeedsRef) unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
+      if constexpr (kNeedsRef) unpack_ref8<kRefF32>(v < ref_nvec ? ld_ref8<kRefF32>(zr, v) : zero_ref8<kRefF32>(), r);
       const int c0 = v << 3;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -431,23 +493,24 @@ __device__ __forceinline__ void npo8_eval(const float (&x)[8], const float (&r)[
   }
 }
 
-template <int kThreads, int kMinBlocks, int kPf2 = 1>
+template <int kThreads, int kMinBlocks, bool kRefF32, int kPf2 = 1>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(const RowLossParams a, const int cache_vecs) {
   extern __shared__ float4 s_cache[];  // [2][cache_vecs]: low / high half of each 8-logit vector (conflict-free float4 rows)
   __shared__ float2 red[32];
   const int64_t row = blockIdx.x;
   __nv_bfloat16* z = a.logits + row * a.ld;
-  const __nv_bfloat16* zr = a.ref_logits + row * a.ref_ld;
+  const char* zr = static_cast<const char*>(a.ref_logits) + row * a.ref_ld * (kRefF32 ? 4 : 2);
   const int nvec = (int)(a.ld >> 3);
   const int nfull = a.vocab >> 3;
   const int ref_nvec = (int)(a.ref_ld >> 3);
   const int ncache = a.write_grad ? min(cache_vecs, nfull) : 0;
   // register double-buffering: the next vector pair is in flight while this one is being evaluated (the first pair
   // while the row statistics are merged)
-  uint4 nx = make_uint4(0, 0, 0, 0), nr = nx;
+  uint4 nx = make_uint4(0, 0, 0, 0);
+  RefVec<kRefF32> nr = zero_ref8<kRefF32>();
   if ((int)threadIdx.x < nfull) {
     nx = reinterpret_cast<const uint4*>(z)[threadIdx.x];
-    nr = reinterpret_cast<const uint4*>(zr)[threadIdx.x];
+    nr = ld_ref8<kRefF32>(zr, threadIdx.x);
   }
   float lse_s, lse_t;
   merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, lse_s, lse_t);
@@ -456,18 +519,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(cons
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
   float stat = 0.f, lossl2 = 0.f;
   for (int v = threadIdx.x; v < nfull; v += kThreads) {
-    const uint4 cx = nx, cr = nr;
+    const uint4 cx = nx;
+    const RefVec<kRefF32> cr = nr;
     if (v + kThreads < nfull) {
       nx = reinterpret_cast<const uint4*>(z)[v + kThreads];
-      nr = reinterpret_cast<const uint4*>(zr)[v + kThreads];
+      nr = ld_ref8<kRefF32>(zr, v + kThreads);
     }
     if (kL2Ahead && v + kL2Ahead * kThreads < nfull) {  // pull the vectors of later iterations into L2 (no register cost)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(z) + v + kL2Ahead * kThreads));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(zr) + v + kL2Ahead * kThreads));
+      prefetch_ref8<kRefF32>(zr, v + kL2Ahead * kThreads);
     }
     float x[8], r[8];
     unpack8(cx, x);
-    unpack8(cr, r);
+    unpack_ref8<kRefF32>(cr, r);
     Npo8 o;
     npo8_eval(x, r, nls2, nlt2, o, stat, lossl2, true);
     if (v < ncache) {
@@ -480,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(cons
     c.nls2 = nls2; c.nlt2 = nlt2; c.dlse = lse_t - lse_s; c.lse_s = lse_s; c.beta = 1.f;
     float x[8], r[8], l = 0.f;
     unpack8(reinterpret_cast<const uint4*>(z)[nfull], x);
-    unpack8(nfull < ref_nvec ? reinterpret_cast<const uint4*>(zr)[nfull] : make_uint4(0, 0, 0, 0), r);
+    unpack_ref8<kRefF32>(nfull < ref_nvec ? ld_ref8<kRefF32>(zr, nfull) : zero_ref8<kRefF32>(), r);
     for (int j = 0; j < (a.vocab & 7); ++j) {
       float p, aux;
       RowTerm<CLEAR_KIND_NPO, true>::eval(x[j], r[j], c, p, aux, stat, l);
@@ -514,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(cons
       for (int j = 0; j < 8; ++j) x[j] = fmaf(-ptx::ex2_approx(fmaf(x[j], kLog2e, nls2)), gS, g * s[j]);
     } else if (v < nfull) {
       float r[8], st = 0.f, ls = 0.f;
-      unpack8(reinterpret_cast<const uint4*>(zr)[v], r);
+      unpack_ref8<kRefF32>(ld_ref8<kRefF32>(zr, v), r);
       Npo8 o;
       npo8_eval(x, r, nls2, nlt2, o, st, ls, false);
 #pragma unroll
@@ -523,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(cons
       RowConsts c;
       c.nls2 = nls2; c.nlt2 = nlt2; c.dlse = lse_t - lse_s; c.lse_s = lse_s; c.beta = 1.f;
       float r[8];
-      unpack8(v < ref_nvec ? reinterpret_cast<const uint4*>(zr)[v] : make_uint4(0, 0, 0, 0), r);
+      unpack_ref8<kRefF32>(v < ref_nvec ? ld_ref8<kRefF32>(zr, v) : zero_ref8<kRefF32>(), r);
       const int c0 = v << 3;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -539,19 +603,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(cons
 // (max, sum-exp) partials of already-materialised logits (teacher logits handed over as a tensor), in
 // the [row][256-column tile] layout the projection's epilogue emits.  One warp per tile: a lane holds
 // 8 consecutive columns (one 128-bit load).
-__global__ void __launch_bounds__(256) lse_partials_kernel(const __nv_bfloat16* logits, int64_t ld, int vocab,
+template <bool kF32>
+__global__ void __launch_bounds__(256) lse_partials_kernel(const void* logits, int64_t ld, int vocab,
                                                            int n_vtiles, float2* part) {
   const int64_t row = blockIdx.x;
-  const __nv_bfloat16* z = logits + row * ld;
+  const char* z = static_cast<const char*>(logits) + row * ld * (kF32 ? 4 : 2);
   const int lane = threadIdx.x & 31;
   for (int t = threadIdx.x >> 5; t < n_vtiles; t += 8) {
     const int c0 = t * 256 + lane * 8;
     float x[8];
     if (c0 + 8 <= vocab) {
-      unpack8(*reinterpret_cast<const uint4*>(z + c0), x);
+      unpack_ref8<kF32>(ld_ref8<kF32>(z, c0 >> 3), x);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = (c0 + j < vocab) ? __bfloat162float(z[c0 + j]) : -INFINITY;
+      for (int j = 0; j < 8; ++j) {
+        float val = -INFINITY;
+        if (c0 + j < vocab) val = kF32 ? reinterpret_cast<const float*>(z)[c0 + j] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(z)[c0 + j]);
+        x[j] = val;
+      }
     }
     float m = x[0];
 #pragma unroll
@@ -567,10 +636,11 @@ __global__ void __launch_bounds__(256) lse_partials_kernel(const __nv_bfloat16* 
 
 // fp32 [rows, cols] (dense) -> bf16 [rows, ld]: the conversion pass after a split-K dH contraction.
 __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* src, __nv_bfloat16* dst, int cols, int64_t ld,
-                                                               int64_t nvec) {
+                                                               int64_t nvec, const int* m_dev, int m_off) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= nvec) return;
   const int vec_per_row = cols >> 3;
+  if (m_dev) nvec = min(nvec, (int64_t)max(*m_dev - m_off, 0) * vec_per_row);
+  if (i >= nvec) return;
   const int64_t row = i / vec_per_row;
   const int c = (int)(i - row * vec_per_row) << 3;
   const float4 a = *reinterpret_cast<const float4*>(src + row * cols + c);
@@ -610,21 +680,49 @@ __global__ void __launch_bounds__(1024) compact_rows_kernel(const int64_t* label
   if (threadIdx.x == 0) *count = carry;
 }
 
+// n_dev: optional device-side number of indices (<= n_idx).  Gather with pad_to > 0: destination rows [n, round_up(n, pad_to))
+// (below n_idx) are zero-filled — they fall into the last K block of the dW contraction.  row_index NULL = identity.
 template <bool kScatter>
 __global__ void __launch_bounds__(256) rows_move_kernel(const uint8_t* src, int64_t src_ld_bytes, const int32_t* row_index,
-                                                        int64_t n_idx, int row_bytes, uint8_t* dst, int64_t dst_ld_bytes) {
+                                                        int64_t n_idx, int row_bytes, uint8_t* dst, int64_t dst_ld_bytes,
+                                                        const int* n_dev, int pad_to) {
   const int lanes_per_row = (row_bytes & 15) ? ((row_bytes + 3) >> 2) : (row_bytes >> 4);
-  const int64_t total = n_idx * lanes_per_row;
+  const int64_t n = n_dev ? min(n_idx, (int64_t)max(*n_dev, 0)) : n_idx;
+  int64_t n_out = n;
+  if (!kScatter && pad_to > 0) n_out = min(n_idx, (n + pad_to - 1) / pad_to * pad_to);
+  const int64_t total = n_out * lanes_per_row;
   const int64_t stride = (int64_t)gridDim.x * 256;
   for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += stride) {
     const int64_t i = t / lanes_per_row;
     const int c = (int)(t - i * lanes_per_row);
-    const int64_t r = row_index[i];
+    if (i >= n) {  // zero padding row (gather only)
+      uint8_t* d = dst + i * dst_ld_bytes;
+      if (row_bytes & 15) reinterpret_cast<uint32_t*>(d)[c] = 0u;
+      else reinterpret_cast<uint4*>(d)[c] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const int64_t r = row_index ? (int64_t)row_index[i] : i;
     const uint8_t* s = src + (kScatter ? i : r) * src_ld_bytes;
     uint8_t* d = dst + (kScatter ? r : i) * dst_ld_bytes;
     if (row_bytes & 15) reinterpret_cast<uint32_t*>(d)[c] = reinterpret_cast<const uint32_t*>(s)[c];
     else reinterpret_cast<uint4*>(d)[c] = reinterpret_cast<const uint4*>(s)[c];
   }
+}
+
+// out[i] = outer[inner[i]] for i < *n_dev: the source row of compacted row i when the rows are also remapped (row_index)
+__global__ void __launch_bounds__(256) compose_index_kernel(const int32_t* inner, const int32_t* outer, int64_t n_max,
+                                                            const int* n_dev, int32_t* out) {
+  const int64_t n = n_dev ? min(n_max, (int64_t)max(*n_dev, 0)) : n_max;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = outer[inner[i]];
+}
+
+// fp32 rows [0, *m_dev - m_off) x cols <- 0 (the split-K scratch of a dH contraction over a device-side row count)
+__global__ void __launch_bounds__(256) zero_rows_f32_kernel(float* dst, int cols, int64_t n_rows_max, const int* m_dev, int m_off) {
+  const int64_t rows = m_dev ? min(n_rows_max, (int64_t)max(*m_dev - m_off, 0)) : n_rows_max;
+  const int64_t nvec = rows * (cols >> 2);
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) reinterpret_cast<float4*>(dst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -716,21 +814,38 @@ int clear_head_project(const ClearProjectArgs* a, void* stream) {
                 (long long)a->logits_ld);
   GemmOperand A{a->hidden, a->hidden_ld, kMajorK};
   GemmOperand B{a->weight, a->weight_ld, kMajorK};
+  GemmDyn dyn;
+  dyn.count = a->n_rows_dev;
+  dyn.offset = a->n_rows_dev_offset;
+  dyn.dim = 1;
   return launch_gemm_bf16(a->cta_group, A, B, a->logits, 0, a->logits_ld, (int)a->n_rows, a->vocab, a->hidden_dim,
-                          a->lse_part, 0, /*raster: traffic model*/ -1, static_cast<cudaStream_t>(stream));
+                          a->lse_part, 0, /*raster: traffic model*/ -1, static_cast<cudaStream_t>(stream), 1, nullptr, 0, dyn);
 }
 
-int clear_head_lse_partials(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
-                            void* stream) {
+static int lse_partials_impl(const void* logits, bool f32, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
+                             void* stream) {
   if (!logits || !lse_part) return fail(CLEAR_ERR_NULL, "clear_head_lse_partials: null pointer");
   if (n_rows <= 0 || n_rows > INT32_MAX || vocab <= 0 || logits_ld < vocab || logits_ld % 8)
     return fail(CLEAR_ERR_SHAPE, "clear_head_lse_partials: bad sizes");
   if (reinterpret_cast<uintptr_t>(logits) & 15) return fail(CLEAR_ERR_ALIGN, "clear_head_lse_partials: logits must be 16-byte aligned");
-  lse_partials_kernel<<<(unsigned)n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(logits), logits_ld, vocab, clear_head_vtiles(vocab),
-      reinterpret_cast<float2*>(lse_part));
+  if (f32)
+    lse_partials_kernel<true><<<(unsigned)n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, logits_ld, vocab, clear_head_vtiles(vocab), reinterpret_cast<float2*>(lse_part));
+  else
+    lse_partials_kernel<false><<<(unsigned)n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, logits_ld, vocab, clear_head_vtiles(vocab), reinterpret_cast<float2*>(lse_part));
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int clear_head_lse_partials(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
+                            void* stream) {
+  return lse_partials_impl(logits, false, logits_ld, n_rows, vocab, lse_part, stream);
+}
+
+int clear_head_lse_partials_f32(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
+                                void* stream) {
+  return lse_partials_impl(logits, true, logits_ld, n_rows, vocab, lse_part, stream);
 }
 
 int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
@@ -752,7 +867,7 @@ int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
   RowLossParams p;
   p.logits = static_cast<__nv_bfloat16*>(a->logits);
   p.lse_part = reinterpret_cast<const float2*>(a->lse_part);
-  p.ref_logits = static_cast<const __nv_bfloat16*>(a->ref_logits);
+  p.ref_logits = a->ref_logits;
   p.ref_lse_part = reinterpret_cast<const float2*>(a->ref_lse_part);
   p.labels = a->labels;
   p.row_weight = a->row_weight;
@@ -765,36 +880,47 @@ int clear_head_rowloss(const ClearRowLossArgs* a, void* stream_) {
   p.grad_scale = a->grad_scale;
   p.beta = a->beta;
   p.write_grad = a->write_grad;
+  p.m_dev = a->n_rows_dev;
+  p.m_off = a->n_rows_dev_offset;
+  p.status_flags = a->status_flags;
+  if (a->n_rows_dev && a->kind != CLEAR_KIND_CE)
+    return fail(CLEAR_ERR_KIND, "clear_head_rowloss: a device-side row count (row compaction) exists for CE only");
+  const bool rf32 = needs_ref && a->ref_logits_f32;
   const unsigned grid = (unsigned)a->n_rows;
   switch (a->kind) {
     case CLEAR_KIND_CE:
       rowloss_ce_kernel<256><<<grid, 256, 0, stream>>>(p);
       break;
     case CLEAR_KIND_KL_FWD:
-      rowloss_klfwd_kernel<256><<<grid, 256, 0, stream>>>(p);
+      if (rf32) rowloss_klfwd_kernel<256, true><<<grid, 256, 0, stream>>>(p);
+      else      rowloss_klfwd_kernel<256, false><<<grid, 256, 0, stream>>>(p);
       break;
     case CLEAR_KIND_KL_REV:
-      rowloss_twopass_kernel<CLEAR_KIND_KL_REV, true, 512><<<grid, 512, 0, stream>>>(p);
+      if (rf32) rowloss_twopass_kernel<CLEAR_KIND_KL_REV, true, 512, true><<<grid, 512, 0, stream>>>(p);
+      else      rowloss_twopass_kernel<CLEAR_KIND_KL_REV, true, 512, false><<<grid, 512, 0, stream>>>(p);
       break;
     case CLEAR_KIND_ENTROPY:
-      rowloss_twopass_kernel<CLEAR_KIND_ENTROPY, true, 512><<<grid, 512, 0, stream>>>(p);
+      rowloss_twopass_kernel<CLEAR_KIND_ENTROPY, true, 512, false><<<grid, 512, 0, stream>>>(p);
       break;
     case CLEAR_KIND_NPO:
       if (a->beta == 1.0f) {
         // 512 threads x 2 CTAs per SM with 96 KB of s-cache each measured best on B200 (tools/gpu_rowloss_ab.py, interleaved
         // A/B per 4096 rows: 203 us; 1024 x 1 with the whole row cached 241 us; 256 x 4 / 48 KB 211 us; 384 x 3 / 64 KB 208 us;
         // deeper register prefetch in either pass 207-217 us)
-        static bool configured = false;
         constexpr int kSmem = kNpoCacheVecs * 32;
-        if (!configured) {
-          CLEAR_CUDA_OK(cudaFuncSetAttribute(rowloss_npo1_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-          configured = true;
-        }
         const int nfull = a->vocab >> 3;
         const int cache_vecs = a->write_grad ? (nfull < kNpoCacheVecs ? nfull : kNpoCacheVecs) : 0;
-        rowloss_npo1_kernel<512, 2><<<grid, 512, (size_t)cache_vecs * 32, stream>>>(p, cache_vecs);
+        // the attribute is per device: set on every launch (a host-side table lookup, no device work)
+        if (rf32) {
+          CLEAR_CUDA_OK(cudaFuncSetAttribute(rowloss_npo1_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+          rowloss_npo1_kernel<512, 2, true><<<grid, 512, (size_t)cache_vecs * 32, stream>>>(p, cache_vecs);
+        } else {
+          CLEAR_CUDA_OK(cudaFuncSetAttribute(rowloss_npo1_kernel<512, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+          rowloss_npo1_kernel<512, 2, false><<<grid, 512, (size_t)cache_vecs * 32, stream>>>(p, cache_vecs);
+        }
       } else {
-        rowloss_twopass_kernel<CLEAR_KIND_NPO, false, 512><<<grid, 512, 0, stream>>>(p);
+        if (rf32) rowloss_twopass_kernel<CLEAR_KIND_NPO, false, 512, true><<<grid, 512, 0, stream>>>(p);
+        else      rowloss_twopass_kernel<CLEAR_KIND_NPO, false, 512, false><<<grid, 512, 0, stream>>>(p);
       }
       break;
     default:
@@ -813,9 +939,11 @@ int clear_head_compact_rows(const int64_t* labels, int64_t n_rows, int32_t* row_
 }
 
 static int rows_move(bool scatter, const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx,
-                     int32_t row_bytes, void* dst, int64_t dst_ld_bytes, void* stream) {
+                     int32_t row_bytes, void* dst, int64_t dst_ld_bytes, void* stream, const int32_t* n_idx_dev = nullptr,
+                     int32_t pad_to = 0, bool identity_ok = false) {
   const char* who = scatter ? "clear_rows_scatter" : "clear_rows_gather";
-  if (!src || !dst || !row_index) return fail(CLEAR_ERR_NULL, "%s: null pointer", who);
+  if (!src || !dst || (!row_index && !identity_ok)) return fail(CLEAR_ERR_NULL, "%s: null pointer", who);
+  if (pad_to < 0) return fail(CLEAR_ERR_SHAPE, "%s: pad_to < 0", who);
   if (n_idx < 0 || row_bytes <= 0 || (row_bytes & 3) || src_ld_bytes < row_bytes || dst_ld_bytes < row_bytes)
     return fail(CLEAR_ERR_SHAPE, "%s: row_bytes must be a positive multiple of 4 within both strides", who);
   const int align = (row_bytes & 15) ? 3 : 15;
@@ -828,10 +956,32 @@ static int rows_move(bool scatter, const void* src, int64_t src_ld_bytes, const 
   if (blocks > cap) blocks = cap;
   if (scatter)
     rows_move_kernel<true><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint8_t*>(src), src_ld_bytes, row_index, n_idx, row_bytes, static_cast<uint8_t*>(dst), dst_ld_bytes);
+        static_cast<const uint8_t*>(src), src_ld_bytes, row_index, n_idx, row_bytes, static_cast<uint8_t*>(dst), dst_ld_bytes,
+        n_idx_dev, 0);
   else
     rows_move_kernel<false><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint8_t*>(src), src_ld_bytes, row_index, n_idx, row_bytes, static_cast<uint8_t*>(dst), dst_ld_bytes);
+        static_cast<const uint8_t*>(src), src_ld_bytes, row_index, n_idx, row_bytes, static_cast<uint8_t*>(dst), dst_ld_bytes,
+        n_idx_dev, pad_to);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_rows_gather_dev(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx_max,
+                          const int32_t* n_idx_dev, int32_t pad_to, int32_t row_bytes, void* dst, int64_t dst_ld_bytes, void* stream) {
+  return rows_move(false, src, src_ld_bytes, row_index, n_idx_max, row_bytes, dst, dst_ld_bytes, stream, n_idx_dev, pad_to, true);
+}
+
+int clear_rows_scatter_dev(const void* src, int64_t src_ld_bytes, const int32_t* row_index, int64_t n_idx_max,
+                           const int32_t* n_idx_dev, int32_t row_bytes, void* dst, int64_t dst_ld_bytes, void* stream) {
+  return rows_move(true, src, src_ld_bytes, row_index, n_idx_max, row_bytes, dst, dst_ld_bytes, stream, n_idx_dev, 0, false);
+}
+
+int clear_index_compose(const int32_t* inner, const int32_t* outer, int64_t n_max, const int32_t* n_dev, int32_t* out, void* stream) {
+  if (!inner || !outer || !out) return fail(CLEAR_ERR_NULL, "clear_index_compose: null pointer");
+  if (n_max <= 0) return fail(CLEAR_ERR_SHAPE, "clear_index_compose: n_max <= 0");
+  int64_t blocks = (n_max + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  compose_index_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(inner, outer, n_max, n_dev, out);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -885,21 +1035,42 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
     // dH[n, h] = sum_v dZ[n, v] W[v, h]: A = dZ (K-major, K = vocab), B = W read MN-major.
     GemmOperand A{a->dlogits, a->dlogits_ld, kMajorK};
     GemmOperand B{a->weight, a->weight_ld, kMajorMN};
-    const int splits = a->dhidden_ws ? gemm_pick_k_splits(a->cta_group, (int)a->n_rows, a->hidden_dim, a->vocab) : 1;
-    if (splits > 1) {
-      const size_t ws_elems = (size_t)a->n_rows * a->hidden_dim;
-      CLEAR_CUDA_OK(cudaMemsetAsync(a->dhidden_ws, 0, ws_elems * sizeof(float), stream));
+    GemmDyn dyn;
+    dyn.count = a->n_rows_dev;
+    dyn.offset = a->n_rows_dev_offset;
+    dyn.dim = 1;
+    if (a->n_rows_dev && a->dhidden_ws) {
+      // Row count known on the device only (row compaction): the number of output tiles, hence the K split that fills the
+      // SMs, is chosen inside the kernel; the fp32 scratch is zeroed / converted for the live rows only.
+      dyn.splits = 1;
+      const int64_t nvec4 = (int64_t)a->n_rows * (a->hidden_dim / 4);
+      zero_rows_f32_kernel<<<(unsigned)std::min<int64_t>((nvec4 + 255) / 256, 148 * 8), 256, 0, stream>>>(
+          a->dhidden_ws, a->hidden_dim, a->n_rows, a->n_rows_dev, a->n_rows_dev_offset);
       rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden_ws, 1, a->hidden_dim, (int)a->n_rows, a->hidden_dim, a->vocab,
-                            nullptr, /*reduce_add=*/1, /*raster: traffic model*/ -1, stream, splits);
+                            nullptr, /*reduce_add=*/1, /*raster: traffic model*/ -1, stream, 1, nullptr, 0, dyn);
       if (rc) return rc;
       const int64_t nvec = (int64_t)a->n_rows * (a->hidden_dim / 8);
       f32_to_bf16_rows_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, stream>>>(
-          a->dhidden_ws, static_cast<__nv_bfloat16*>(a->dhidden), a->hidden_dim, a->dhidden_ld, nvec);
+          a->dhidden_ws, static_cast<__nv_bfloat16*>(a->dhidden), a->hidden_dim, a->dhidden_ld, nvec, a->n_rows_dev,
+          a->n_rows_dev_offset);
       CLEAR_CUDA_OK(cudaGetLastError());
     } else {
-      rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden, 0, a->dhidden_ld, (int)a->n_rows, a->hidden_dim, a->vocab,
-                            nullptr, 0, /*raster: traffic model*/ -1, stream);
-      if (rc) return rc;
+      const int splits = (a->dhidden_ws && !a->n_rows_dev) ? gemm_pick_k_splits(a->cta_group, (int)a->n_rows, a->hidden_dim, a->vocab) : 1;
+      if (splits > 1) {
+        const size_t ws_elems = (size_t)a->n_rows * a->hidden_dim;
+        CLEAR_CUDA_OK(cudaMemsetAsync(a->dhidden_ws, 0, ws_elems * sizeof(float), stream));
+        rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden_ws, 1, a->hidden_dim, (int)a->n_rows, a->hidden_dim, a->vocab,
+                              nullptr, /*reduce_add=*/1, /*raster: traffic model*/ -1, stream, splits);
+        if (rc) return rc;
+        const int64_t nvec = (int64_t)a->n_rows * (a->hidden_dim / 8);
+        f32_to_bf16_rows_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, stream>>>(
+            a->dhidden_ws, static_cast<__nv_bfloat16*>(a->dhidden), a->hidden_dim, a->dhidden_ld, nvec, nullptr, 0);
+        CLEAR_CUDA_OK(cudaGetLastError());
+      } else {
+        rc = launch_gemm_bf16(a->cta_group, A, B, a->dhidden, 0, a->dhidden_ld, (int)a->n_rows, a->hidden_dim, a->vocab,
+                              nullptr, 0, /*raster: traffic model*/ -1, stream, 1, nullptr, 0, dyn);
+        if (rc) return rc;
+      }
     }
   }
   if (a->dweight || a->n_peers > 0) {
@@ -910,9 +1081,13 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
     GemmOperand A{a->dlogits, a->dlogits_ld, kMajorMN};
     GemmOperand B{a->hidden, a->hidden_ld, kMajorMN};
     void* d = a->dweight ? a->dweight : a->dweight_peers[0];
+    GemmDyn dyn;   // K = rows: with a device-side count, the rows of dlogits / hidden up to the next multiple of 64 are zero
+    dyn.count = a->n_rows_dev;
+    dyn.offset = a->n_rows_dev_offset;
+    dyn.dim = 2;
     rc = launch_gemm_bf16(a->cta_group, A, B, d, a->dweight_f32, a->dweight_ld, a->vocab, a->hidden_dim,
                           (int)a->n_rows, nullptr, a->accumulate, /*raster: traffic model*/ -1, stream, 1,
-                          a->n_peers > 0 ? a->dweight_peers : nullptr, a->n_peers);
+                          a->n_peers > 0 ? a->dweight_peers : nullptr, a->n_peers, dyn);
     if (rc) return rc;
   }
   return 0;

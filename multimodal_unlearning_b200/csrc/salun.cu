@@ -306,6 +306,122 @@ __global__ void __launch_bounds__(1024) select_kernel(const uint32_t* hist, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Global-threshold scope (upstream SalUn's global rank; SURVEY.md App. B #11, north_star "a global threshold"): ONE ranking
+// over all tensors.  The per-tensor histograms above already hold everything needed:
+//   hist_total          total[b] = sum_s hist[s][b]  (zero padding of every tensor taken out of bin 0) — with the flat
+//                       buffer sharded over ranks, the caller all-reduces `total` (256 KB of int64) here;
+//   select_global_tau   tau_j = key of the k_j-th largest element overall, k_j = int(th_j * total numel), and the tie budget;
+//   select_global_fill  per tensor the same (tau, ties, lo, hi, total) record the per-tensor select writes, with the
+//                       global tie budget handed out in flat index order: tensor s takes
+//                       clamp(budget - #ties in earlier tensors, 0, #ties in s).
+// The mask pass is unchanged: it consumes the per-tensor records.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hist_total_kernel(const uint32_t* hist, const int64_t* seg_off, const int64_t* seg_numel,
+                                                         int n_segs, long long* total) {
+  const int b = blockIdx.x * 256 + threadIdx.x;  // one bin per thread; a warp reads 128 contiguous bytes per tensor
+  long long t = 0;
+  for (int s = 0; s < n_segs; ++s) t += hist[(size_t)s * kBins + b];
+  if (b == 0 && seg_numel)
+    for (int s = 0; s < n_segs; ++s) t -= (seg_off[s + 1] - seg_off[s]) - seg_numel[s];
+  total[b] = t;
+}
+
+__global__ void __launch_bounds__(1024) select_global_tau_kernel(const long long* total, long long n_total, SelectTargets tg,
+                                                                 int64_t* tau_budget) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long wbase[32];
+  const int hi = kBins - 1 - 32 * (int)threadIdx.x;  // thread t owns the 32 bins [hi-31, hi], descending
+  unsigned long long local = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) local += (unsigned long long)total[hi - i];
+  unsigned long long incl = local;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long v = wsum[lane], s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += u;
+    }
+    wbase[lane] = s - v;
+  }
+  __syncthreads();
+  const unsigned long long above0 = wbase[warp] + incl - local;  // #{key > hi}
+  for (int j = 0; j < tg.n; ++j) {
+    long long k = (long long)(tg.th[j] * (double)n_total);  // int(threshold * num_elements), generate_mask.py:69
+    if (k > n_total) k = n_total;
+    if (k <= 0) {
+      if (threadIdx.x == 0) { tau_budget[2 * j] = -1; tau_budget[2 * j + 1] = 0; }
+      continue;
+    }
+    if ((unsigned long long)k > above0 && (unsigned long long)k <= above0 + local) {
+      unsigned long long above = above0;
+      for (int i = 0; i < 32; ++i) {
+        const unsigned long long c = (unsigned long long)total[hi - i];
+        if ((unsigned long long)k <= above + c) {
+          tau_budget[2 * j] = hi - i;
+          tau_budget[2 * j + 1] = (int64_t)((unsigned long long)k - above);
+          break;
+        }
+        above += c;
+      }
+    }
+  }
+}
+
+// One CTA per threshold: exclusive scan, in tensor order, of the tensors' tie counts against the budget.
+__global__ void __launch_bounds__(1024) select_global_fill_kernel(const uint32_t* hist, const int64_t* seg_off,
+                                                                  const int64_t* seg_numel, int n_segs, const int64_t* tau_budget,
+                                                                  const int64_t* budget_override, int n_th, int64_t* select) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long carry;
+  const int j = blockIdx.x;
+  const int64_t tau = tau_budget[2 * j];
+  const unsigned long long budget = (unsigned long long)(budget_override ? budget_override[j] : tau_budget[2 * j + 1]);
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_segs; base += 1024) {
+    const int s = base + (int)threadIdx.x;
+    unsigned long long c = 0;
+    if (s < n_segs && tau >= 0) {
+      c = hist[(size_t)s * kBins + tau];
+      if (tau == 0 && seg_numel) c -= (unsigned long long)((seg_off[s + 1] - seg_off[s]) - seg_numel[s]);
+    }
+    unsigned long long incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long wb = 0;
+    for (int w = 0; w < warp; ++w) wb += wsum[w];
+    const unsigned long long excl = carry + wb + incl - c;
+    if (s < n_segs) {
+      int64_t* out = select + ((size_t)s * n_th + j) * kSelFields;
+      if (tau < 0) {
+        write_select(out, -1, 0, 0);
+      } else {
+        const unsigned long long left = budget > excl ? budget - excl : 0ull;
+        write_select(out, tau, (int64_t)(left < c ? left : c), (int64_t)c);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + c;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Mask.  Chunks of 8192 elements never straddle tensors (chunk_prefix[s] = number of chunks before
 // tensor s).  Flat order inside a chunk is (iter, thread, lane-in-vector), loads stay coalesced.
 // ------------------------------------------------------------------------------------------------
@@ -693,6 +809,16 @@ __global__ void __launch_bounds__(256) mask_unpack_kernel(const uint8_t* bits, i
   }
 }
 
+// diagnostic override of the lane-private window (CLEAR_HIST_WIN, read once, clamped to what the kernel allocates)
+int hist_window_slots() {
+  static const int slots = [] {
+    const char* e = getenv("CLEAR_HIST_WIN");
+    int v = e ? atoi(e) : kWinSlots;
+    return v < 0 ? 0 : (v > kWinSlots ? kWinSlots : v);
+  }();
+  return slots;
+}
+
 int stream_grid(int64_t nvec, int threads) {
   const int sms = device_sm_count();
   int64_t blocks = (nvec + threads - 1) / threads;
@@ -752,18 +878,14 @@ int clear_saliency_histogram(const void* acc, const int64_t* seg_offsets_dev, in
   if (!acc || !seg_offsets_dev || !hist) return fail(CLEAR_ERR_NULL, "clear_saliency_histogram: null pointer");
   if (n_segs <= 0 || n_total <= 0 || (n_total & 7)) return fail(CLEAR_ERR_SHAPE, "clear_saliency_histogram: n_total must be a positive multiple of 8");
   if (reinterpret_cast<uintptr_t>(acc) & 15) return fail(CLEAR_ERR_ALIGN, "clear_saliency_histogram: acc must be 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
-    CLEAR_CUDA_OK(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
-    configured = true;
-  }
+  CLEAR_CUDA_OK(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));  // per device: set every time
   const int sms = device_sm_count();
   int64_t blocks = sms > 0 ? sms : 148;
   int64_t per_block = ((n_total + blocks - 1) / blocks + 4095) / 4096 * 4096;
   blocks = (n_total + per_block - 1) / per_block;
   histogram_kernel<<<(unsigned)blocks, kHistThreads, kHistSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(acc), seg_offsets_dev, n_segs, n_total, per_block, hist,
-      getenv("CLEAR_HIST_WIN") ? atoi(getenv("CLEAR_HIST_WIN")) : kWinSlots);
+      hist_window_slots());
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -776,6 +898,41 @@ int clear_saliency_select(const uint32_t* hist, const int64_t* seg_offsets_dev, 
   tg.n = n_th;
   for (int j = 0; j < n_th; ++j) tg.th[j] = thresholds_host[j];
   select_kernel<<<(unsigned)n_segs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(hist, seg_offsets_dev, seg_numel_dev, tg, select);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_saliency_hist_total(const uint32_t* hist, const int64_t* seg_offsets_dev, const int64_t* seg_numel_dev, int32_t n_segs,
+                              int64_t* total, void* stream) {
+  if (!hist || !seg_offsets_dev || !total) return fail(CLEAR_ERR_NULL, "clear_saliency_hist_total: null pointer");
+  if (n_segs <= 0) return fail(CLEAR_ERR_SHAPE, "clear_saliency_hist_total: n_segs <= 0");
+  hist_total_kernel<<<kBins / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, seg_offsets_dev, seg_numel_dev, n_segs,
+                                                                               reinterpret_cast<long long*>(total));
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_saliency_select_global_tau(const int64_t* total, int64_t n_total, const double* thresholds_host, int32_t n_th,
+                                     int64_t* tau_budget, void* stream) {
+  if (!total || !thresholds_host || !tau_budget) return fail(CLEAR_ERR_NULL, "clear_saliency_select_global_tau: null pointer");
+  if (n_total <= 0 || n_th <= 0 || n_th > kMaxThresholds)
+    return fail(CLEAR_ERR_SHAPE, "clear_saliency_select_global_tau: n_total > 0 and 1 <= n_th <= %d required", kMaxThresholds);
+  SelectTargets tg;
+  tg.n = n_th;
+  for (int j = 0; j < n_th; ++j) tg.th[j] = thresholds_host[j];
+  select_global_tau_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(total),
+                                                                              (long long)n_total, tg, tau_budget);
+  CLEAR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int clear_saliency_select_global_fill(const uint32_t* hist, const int64_t* seg_offsets_dev, const int64_t* seg_numel_dev,
+                                      int32_t n_segs, const int64_t* tau_budget, const int64_t* budget_override, int32_t n_th,
+                                      int64_t* select, void* stream) {
+  if (!hist || !seg_offsets_dev || !tau_budget || !select) return fail(CLEAR_ERR_NULL, "clear_saliency_select_global_fill: null pointer");
+  if (n_segs <= 0 || n_th <= 0 || n_th > kMaxThresholds) return fail(CLEAR_ERR_SHAPE, "clear_saliency_select_global_fill: bad sizes");
+  select_global_fill_kernel<<<(unsigned)n_th, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      hist, seg_offsets_dev, seg_numel_dev, n_segs, tau_budget, budget_override, n_th, select);
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -35,9 +35,6 @@ _NEEDS_REF = (KIND_KL_FWD, KIND_KL_REV, KIND_NPO)
 # 8192-row blocks 6.46 ms, 4096-row blocks 6.93 ms, 2048-row blocks 7.43 ms — fewer blocks mean fewer re-reads of W,
 # fewer read-modify-write passes over dW and fuller waves of output tiles in the dH contraction.
 DEFAULT_BLOCK_ROWS = 8192
-# compact_ignored gathers the valid rows only when at most this fraction of the rows is valid: above it the gather / scatter
-# passes (2 x N x H x 2 bytes each way) cost more than the skipped rows save.
-COMPACT_MAX_FRACTION = 0.9
 # Up to this many row blocks accumulate dW directly in bf16; beyond it an fp32 accumulator is used and converted once.
 MAX_BF16_ACCUM_BLOCKS = 4
 
@@ -137,7 +134,8 @@ def rowloss(kind: int, logits: torch.Tensor, lse_part: torch.Tensor, loss_rows: 
                          ref_lse_part=_ptr(ref_lse_part), labels=_ptr(labels), row_weight=_ptr(row_weight),
                          scale_dev=_ptr(scale_dev), loss_rows=loss_rows.data_ptr(), logits_ld=logits.stride(0),
                          ref_ld=ref_logits.stride(0) if ref_logits is not None else 0, n_rows=logits.shape[0],
-                         vocab=vocab, kind=kind, grad_scale=grad_scale, beta=beta, write_grad=int(write_grad))
+                         vocab=vocab, kind=kind, grad_scale=grad_scale, beta=beta, write_grad=int(write_grad),
+                         ref_logits_f32=int(ref_logits is not None and ref_logits.dtype == torch.float32))
     _timed("rowloss", lambda: _lib.check(lib.clear_head_rowloss(C.byref(a), _stream()), "clear_head_rowloss"))
 
 
@@ -273,7 +271,8 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
                       row_weight: torch.Tensor | None = None, need_dhidden: bool = True, need_dweight: bool = True,
                       dweight_accum: torch.Tensor | None = None, block_rows: int | None = None,
                       cta_group: int = 0, overlap: bool = False, dweight_target=None,
-                      compact_ignored: bool = False) -> HeadResult:
+                      compact_ignored: bool = False, row_index: torch.Tensor | None = None,
+                      status_flags: torch.Tensor | None = None) -> HeadResult:
     """One head invocation: loss = coef * norm * sum_i term_i, plus d loss/d hidden and d loss/d weight.
 
     hidden [N, H] bf16, weight [V, H] bf16; labels [N] int64 ALREADY SHIFTED (see shift_labels) for CE;
@@ -287,21 +286,33 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     averaged gradient comes from `reducer.finish(target)`).
     compact_ignored (CE only): run the head on the rows whose label is not -100 only.  Ignored rows contribute nothing to
     the loss, to dW or to their own dH (their dH rows are returned as zeros), so loss and gradients are those of the full
-    evaluation; in CLEAR's batches (padding + 576 image positions + question ignored) this removes most of the work.  Costs
-    one host read of the valid-row count (a synchronisation) — the trainers enable it, a bare call does not.
+    evaluation; in CLEAR's batches (padding + 576 image positions + question ignored) this removes most of the work.  The
+    valid rows are compacted on the device and their count stays there (every kernel reads it from device memory): no host
+    synchronisation.
+    row_index: optional int32 [N] row map (`remove_image_tokens`, mm/trainer_utils.py:48-70, as a kernel input): row i of the
+    invocation is row row_index[i] of hidden / ref_hidden, which may then have more than N rows; dhidden has hidden's shape,
+    rows no index names are zero.  labels / ref_logits / row_weight / loss_rows have N entries.
+    ref_logits may be bf16 or fp32.
+    status_flags: optional int32 [1] device tensor, OR-ed: bit 0 = a CE label outside [0, V) (where torch would assert).
     overlap: issue the contractions and the row passes on two streams (see the staging comment below).  Off
     by default: under the 1 kW power cap the step is energy-bound and the overlap measured no gain on B200.
     """
     lib = _lib.load()
     hidden = _check_2d_bf16(hidden, "hidden")
     weight = _check_2d_bf16(weight, "weight")
-    n, h = hidden.shape
+    n_src, h = hidden.shape
+    n = n_src
     v = weight.shape[0]
     if weight.shape[1] != h:
         raise RuntimeError(f"weight {tuple(weight.shape)} does not match hidden {tuple(hidden.shape)}")
-    if n == 0:
-        raise RuntimeError("head_loss_fwd_bwd: empty batch (N = 0 rows)")
     dev = hidden.device
+    if row_index is not None:
+        if not row_index.is_cuda or row_index.dim() != 1:
+            raise RuntimeError("row_index must be a 1-D CUDA tensor of row numbers of `hidden`")
+        row_index = row_index.to(torch.int32).contiguous()
+        n = row_index.numel()
+    if n == 0 or n_src == 0:
+        raise RuntimeError("head_loss_fwd_bwd: empty batch (N = 0 rows)")
     needs_ref = kind in _NEEDS_REF
     if kind not in KIND_NAMES:
         raise ValueError(f"unknown loss kind {kind}")
@@ -314,9 +325,15 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
             if ref_hidden.shape != hidden.shape or ref_weight.shape != weight.shape:
                 raise RuntimeError("teacher shapes differ from the student's")
         else:
-            ref_logits = _check_2d_bf16(ref_logits, "ref_logits")
+            if ref_logits.dtype == torch.float32:
+                if not ref_logits.is_cuda or ref_logits.dim() != 2 or ref_logits.stride(1) != 1:
+                    raise RuntimeError("ref_logits must be a 2-D row-major CUDA tensor")
+            else:
+                ref_logits = _check_2d_bf16(ref_logits, "ref_logits")
             if ref_logits.shape[0] != n or ref_logits.shape[1] < v:
                 raise RuntimeError("ref_logits must be [N, >= V]")
+            if ref_logits.stride(0) % 8 or ref_logits.data_ptr() % 16:
+                ref_logits = torch.nn.functional.pad(ref_logits, (0, (-ref_logits.shape[1]) % 8)).contiguous()
     if kind == KIND_CE:
         if labels is None:
             raise RuntimeError("CE needs labels")
@@ -328,32 +345,10 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         if row_weight.numel() != n:
             raise RuntimeError("row_weight must have one entry per row")
 
-    if compact_ignored and kind == KIND_CE:
-        idx, cnt = compact_rows(labels)
-        n_valid = int(cnt.item())                     # the one host synchronisation of this mode
-        if 0 < n_valid <= COMPACT_MAX_FRACTION * n:
-            sub_reduction, sub_coef = reduction, coef
-            if reduction == "seq_mean":               # per-sequence sums are rebuilt from the scattered row terms below
-                if not n_seqs or n % n_seqs:
-                    raise RuntimeError("reduction='seq_mean' needs n_seqs dividing the number of rows")
-                sub_reduction, sub_coef = "sum", coef / n_seqs
-            sub = head_loss_fwd_bwd(gather_rows(hidden, idx, n_valid), weight, kind, labels=gather_rows(labels, idx, n_valid),
-                                    beta=beta, coef=sub_coef, reduction=sub_reduction,
-                                    row_weight=gather_rows(row_weight, idx, n_valid) if row_weight is not None else None,
-                                    need_dhidden=need_dhidden, need_dweight=need_dweight, dweight_accum=dweight_accum,
-                                    block_rows=block_rows, cta_group=cta_group, overlap=overlap, dweight_target=dweight_target)
-            loss_rows = scatter_rows(sub.loss_rows, idx, n_valid, n)
-            seq_loss = None
-            launches = sub.launches + 3 + (1 if row_weight is not None else 0) + 1
-            if n_seqs:
-                seq_loss = torch.empty(n_seqs, dtype=torch.float32, device=dev)
-                reduce_sequences(loss_rows, n_seqs, seq_loss)
-                launches += 1
-            dh = None
-            if need_dhidden:
-                dh = scatter_rows(sub.dhidden, idx, n_valid, n)
-                launches += 1
-            return HeadResult(sub.loss, seq_loss, dh, sub.dweight, loss_rows, launches)
+    compact_ignored = bool(compact_ignored) and kind == KIND_CE
+    if status_flags is not None and (status_flags.dtype != torch.int32 or not status_flags.is_cuda or status_flags.numel() < 1):
+        raise RuntimeError("status_flags must be a CUDA int32 tensor")
+    mapped = compact_ignored or row_index is not None
 
     write_grad = need_dhidden or need_dweight
     blk = min(n, block_rows or DEFAULT_BLOCK_ROWS)
@@ -363,8 +358,8 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     launches = 0
 
     host_scale, grad_scale, per_valid = _normalisation(kind, reduction, n, v, beta, n_seqs)
-    pipelined = overlap and n_blocks >= 2 and StageTimer.active is None
-    one_call = not pipelined and StageTimer.active is None
+    pipelined = overlap and n_blocks >= 2 and StageTimer.active is None and not mapped
+    one_call = not pipelined and (StageTimer.active is None or mapped)   # row maps live in the one-call entry only
     inv_count = None
     if per_valid and not one_call:
         inv_count = torch.empty(1, dtype=torch.float32, device=dev)
@@ -384,7 +379,7 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         if ref_logits is None:
             zr = torch.empty((blk, ld), dtype=torch.bfloat16, device=dev)
     loss_rows = torch.empty(n, dtype=torch.float32, device=dev)
-    dhidden = torch.empty_like(hidden) if need_dhidden else None
+    dhidden = torch.empty_like(hidden) if need_dhidden else None     # [n_src, H]: the shape of `hidden`
     dweight = None
     peers = None
     if dweight_target is not None:
@@ -392,6 +387,8 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
             raise RuntimeError("dweight_target needs need_dweight=True and excludes dweight_accum")
         if tuple(dweight_target.shape) != tuple(weight.shape):
             raise RuntimeError("dweight_target was created for a different weight shape")
+        if cta_group not in (0, getattr(dweight_target, "cta_group", 0)):
+            raise RuntimeError("dweight_target: the owners' slabs were cut for the default CTA grouping; pass cta_group=0")
         peers = dweight_target.peer_ptrs
     elif need_dweight:
         if dweight_accum is not None:
@@ -406,6 +403,10 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
             dweight = torch.empty(weight.shape, dtype=torch.float32, device=dev)
 
     launches += n_blocks * (2 + int(needs_ref) + (int(need_dhidden) + int(need_dweight) if write_grad else 0)) + 1 + int(bool(n_seqs))
+    if compact_ignored:   # compact, gather labels (+ row weights), gather hidden, scatter loss terms (+ dH); per block: zero + convert of dH
+        launches += 4 + int(row_weight is not None) + int(row_index is not None) + int(need_dhidden) * (1 + 2 * n_blocks)
+    elif row_index is not None:
+        launches += 1 + int(needs_ref and ref_logits is None) + int(need_dhidden)
     if one_call:
         # The whole invocation in ONE C call (clear_head_loss_fwd_bwd): the block loop, the normalisations and the
         # workspace carving run in the library; this function only owns the tensors.
@@ -428,15 +429,19 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
                           dweight_ld=dweight.stride(0) if dweight is not None else h, n_rows=n, hidden_dim=h, vocab=v, kind=kind,
                           beta=beta, coef=coef, reduction=red, n_seqs=n_seqs or 0, block_rows=blk,
                           dweight_f32=int(dweight is not None and dweight.dtype == torch.float32),
-                          dweight_accumulate=int(dweight_accum is not None), cta_group=cta_group)
+                          dweight_accumulate=int(dweight_accum is not None), cta_group=cta_group,
+                          row_index=_ptr(row_index), n_src_rows=n_src, compact_ignored=int(compact_ignored),
+                          ref_logits_f32=int(needs_ref and ref_logits is not None and ref_logits.dtype == torch.float32),
+                          status_flags=_ptr(status_flags))
         if peers:
             for r, ptr in enumerate(peers):
                 a.dweight_peers[r] = ptr
+            # owners zeroed their slabs, all ranks agreed: the library waits on this event right before the dW contraction,
+            # so the projections and the row pass do not wait for the previous step's all-gather
+            a.dweight_ready_event = dweight_target.ready.cuda_event
         need = C.c_size_t()
         _lib.check(lib.clear_head_loss_workspace_bytes(C.byref(a), C.byref(need)), "clear_head_loss_workspace_bytes")
         ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
-        if peers:
-            torch.cuda.current_stream().wait_event(dweight_target.ready)   # owners zeroed their slabs, all ranks agreed
         _lib.check(lib.clear_head_loss_fwd_bwd(C.byref(a), ws.data_ptr(), need.value, _stream()), "clear_head_loss_fwd_bwd")
         if need_dweight and peers is None and dweight_accum is None and dweight.dtype != torch.bfloat16:
             dweight = dweight.to(torch.bfloat16)
@@ -538,10 +543,11 @@ def _gemm_stream(dev: torch.device) -> "torch.cuda.Stream":
 
 
 def _ref_lse(ref_logits: torch.Tensor, lse_part: torch.Tensor, vocab: int) -> None:
-    """(max, sum-exp) partials of materialised teacher logits, in the layout the projection emits."""
+    """(max, sum-exp) partials of materialised teacher logits (bf16 or fp32), in the layout the projection emits."""
     lib = _lib.load()
-    _lib.check(lib.clear_head_lse_partials(ref_logits.data_ptr(), ref_logits.stride(0), ref_logits.shape[0], vocab,
-                                           lse_part.data_ptr(), _stream()), "clear_head_lse_partials")
+    fn = lib.clear_head_lse_partials_f32 if ref_logits.dtype == torch.float32 else lib.clear_head_lse_partials
+    _lib.check(fn(ref_logits.data_ptr(), ref_logits.stride(0), ref_logits.shape[0], vocab, lse_part.data_ptr(), _stream()),
+               "clear_head_lse_partials")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -551,15 +557,16 @@ def _ref_lse(ref_logits: torch.Tensor, lse_part: torch.Tensor, vocab: int) -> No
 def head_loss_op(hidden: torch.Tensor, weight: torch.Tensor, kind: int, labels: torch.Tensor | None,
                  ref_hidden: torch.Tensor | None, ref_weight: torch.Tensor | None, ref_logits: torch.Tensor | None,
                  row_weight: torch.Tensor | None, beta: float, coef: float, reduction: str, n_seqs: int, block_rows: int,
-                 need_dhidden: bool, need_dweight: bool,
-                 compact_ignored: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(loss [1] fp32, seq_loss [n_seqs] fp32, dhidden [N, H] bf16, dweight [V, H] bf16, loss_rows [N] fp32) of one
-    head invocation; outputs that were not requested come back as empty tensors.  hidden [N, H], weight [V, H] bf16 CUDA;
-    labels shifted, flat.  n_seqs = 0 / block_rows = 0 mean "none" / "default"."""
+                 need_dhidden: bool, need_dweight: bool, compact_ignored: bool,
+                 row_index: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(loss [1] fp32, seq_loss [n_seqs] fp32, dhidden [rows of hidden, H] bf16, dweight [V, H] bf16, loss_rows [N] fp32) of
+    one head invocation; outputs that were not requested come back as empty tensors.  hidden [N or more, H], weight [V, H]
+    bf16 CUDA; labels shifted, flat; row_index int32 [N] optional row map into hidden.  n_seqs = 0 /
+    block_rows = 0 mean "none" / "default"."""
     res = head_loss_fwd_bwd(hidden, weight, kind, labels=labels, ref_hidden=ref_hidden, ref_weight=ref_weight,
                             ref_logits=ref_logits, beta=beta, coef=coef, reduction=reduction, n_seqs=n_seqs or None,
                             row_weight=row_weight, need_dhidden=need_dhidden, need_dweight=need_dweight,
-                            block_rows=block_rows or None, compact_ignored=compact_ignored)
+                            block_rows=block_rows or None, compact_ignored=compact_ignored, row_index=row_index)
     none = lambda dt: torch.empty(0, dtype=dt, device=hidden.device)
     return (res.loss, res.seq_loss if res.seq_loss is not None else none(torch.float32),
             res.dhidden if res.dhidden is not None else none(torch.bfloat16),
@@ -568,12 +575,12 @@ def head_loss_op(hidden: torch.Tensor, weight: torch.Tensor, kind: int, labels: 
 
 @head_loss_op.register_fake
 def _(hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, row_weight, beta, coef, reduction, n_seqs, block_rows,
-      need_dhidden, need_dweight, compact_ignored):
+      need_dhidden, need_dweight, compact_ignored, row_index):
     f32 = dict(dtype=torch.float32, device=hidden.device)
     return (torch.empty(1, **f32), torch.empty(n_seqs, **f32),
             torch.empty_like(hidden) if need_dhidden else torch.empty(0, dtype=torch.bfloat16, device=hidden.device),
             torch.empty_like(weight) if need_dweight else torch.empty(0, dtype=torch.bfloat16, device=hidden.device),
-            torch.empty(hidden.shape[0], **f32))
+            torch.empty(hidden.shape[0] if row_index is None else row_index.shape[0], **f32))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -596,7 +603,7 @@ class _FusedHeadLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, beta, coef, reduction, n_seqs,
-                row_weight, block_rows, compact_ignored):
+                row_weight, block_rows, compact_ignored, row_index):
         shape = hidden.shape
         h2 = hidden.reshape(-1, shape[-1])
         cast = h2.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16
@@ -604,14 +611,17 @@ class _FusedHeadLoss(torch.autograd.Function):
         wb = weight.to(torch.bfloat16).contiguous()
         rh = ref_hidden.reshape(-1, shape[-1]).to(torch.bfloat16).contiguous() if ref_hidden is not None else None
         rw = ref_weight.to(torch.bfloat16).contiguous() if ref_weight is not None else None
-        rl = ref_logits.reshape(-1, ref_logits.shape[-1]).to(torch.bfloat16).contiguous() if ref_logits is not None else None
+        rl = None
+        if ref_logits is not None:   # fp32 teacher logits are consumed as fp32 (no rounding to bf16), anything else as bf16
+            rl = ref_logits.reshape(-1, ref_logits.shape[-1])
+            rl = (rl if rl.dtype == torch.float32 else rl.to(torch.bfloat16)).contiguous()
         reducer = _DW_REDUCER if (ctx.needs_input_grad[1] and _DW_REDUCER is not None
                                   and tuple(_DW_REDUCER.shape) == tuple(wb.shape)) else None
         if reducer is None:
             # through the registered operator (torch.ops.clear_b200.head_loss)
             loss, seq_loss, dh, dw, _rows = torch.ops.clear_b200.head_loss(
                 hb, wb, kind, labels, rh, rw, rl, row_weight, beta, coef, reduction, n_seqs or 0, block_rows or 0,
-                ctx.needs_input_grad[0], ctx.needs_input_grad[1], compact_ignored)
+                ctx.needs_input_grad[0], ctx.needs_input_grad[1], compact_ignored, row_index)
             res = HeadResult(loss, seq_loss if n_seqs else None, dh if dh.numel() else None, dw if dw.numel() else None, _rows, 0)
         else:
             # the fused data-parallel reducer hands the contraction a set of peer buffers: a Python object, outside the
@@ -620,16 +630,29 @@ class _FusedHeadLoss(torch.autograd.Function):
             res = head_loss_fwd_bwd(hb, wb, kind, labels=labels, ref_hidden=rh, ref_weight=rw, ref_logits=rl, beta=beta,
                                     coef=coef, reduction=reduction, n_seqs=n_seqs, row_weight=row_weight,
                                     need_dhidden=ctx.needs_input_grad[0], need_dweight=ctx.needs_input_grad[1],
-                                    block_rows=block_rows, dweight_target=target, compact_ignored=compact_ignored)
+                                    block_rows=block_rows, dweight_target=target, compact_ignored=compact_ignored,
+                                    row_index=row_index)
         dh = res.dhidden.reshape(shape) if res.dhidden is not None else None
         dw = res.dweight
+        ctx.fused = None
         if reducer is not None:
+            pin = reducer.can_hold()
+            if pin:
+                # autograd keeps the reduced gradient where the all-gather wrote it: the buffer is pinned until backward ran;
+                # the main stream does not wait for the all-gather here (backward does), so it overlaps what follows
+                reducer.hold(target.index)
             done, buf = reducer.finish(target)
-            torch.cuda.current_stream().wait_event(done)
-            dw = buf.clone()  # the symmetric buffer is reused two invocations later; autograd may hold dW longer
+            if pin:
+                ctx.fused = (reducer, target.index, done)
+                dw = buf
+            else:
+                torch.cuda.current_stream().wait_event(done)
+                dw = buf.clone()  # more invocations in flight than buffers to pin: take a private copy
         if cast:
             dh = dh.to(hidden.dtype) if dh is not None else None
-            dw = dw.to(weight.dtype) if dw is not None else None
+            if ctx.fused is None:
+                dw = dw.to(weight.dtype) if dw is not None else None
+        ctx.weight_dtype = weight.dtype
         ctx.save_for_backward(dh, dw)
         ctx.mark_non_differentiable(*( [res.seq_loss] if res.seq_loss is not None else [] ))
         if res.seq_loss is not None:
@@ -641,28 +664,38 @@ class _FusedHeadLoss(torch.autograd.Function):
         dh, dw = ctx.saved_tensors
         g = g.to(torch.float32)
         gh = (dh * g.to(dh.dtype)) if dh is not None else None
-        gw = (dw * g.to(dw.dtype)) if dw is not None else None
-        return (gh, gw) + (None,) * 12
+        if ctx.fused is not None:
+            reducer, index, done = ctx.fused
+            torch.cuda.current_stream().wait_event(done)        # the all-gather of this invocation's gradient
+            gw = (dw * g.to(dw.dtype)).to(ctx.weight_dtype)     # a new tensor: the pinned buffer can rotate again
+            reducer.release(index)
+            ctx.fused = None
+        else:
+            gw = (dw * g.to(dw.dtype)) if dw is not None else None
+        return (gh, gw) + (None,) * 13
 
 
 def fused_head_loss(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, labels: torch.Tensor | None = None,
                     ref_hidden: torch.Tensor | None = None, ref_weight: torch.Tensor | None = None,
                     ref_logits: torch.Tensor | None = None, beta: float = 1.0, coef: float = 1.0,
                     reduction: str = "reference", n_seqs: int | None = None, row_weight: torch.Tensor | None = None,
-                    block_rows: int | None = None, compact_ignored: bool = False):
-    """Differentiable loss of one head invocation.  hidden [..., H]; labels already shifted, flat.
+                    block_rows: int | None = None, compact_ignored: bool = False, row_index: torch.Tensor | None = None):
+    """Differentiable loss of one head invocation.  hidden [..., H]; labels already shifted, flat; row_index: optional flat
+    int32 row map into hidden.reshape(-1, H) (see head_loss_fwd_bwd).
     Returns a 0-dim fp32 tensor (and the per-sequence sums when n_seqs is given)."""
     return _FusedHeadLoss.apply(hidden, weight, kind, labels, ref_hidden, ref_weight, ref_logits, float(beta),
-                                float(coef), reduction, n_seqs, row_weight, block_rows, bool(compact_ignored))
+                                float(coef), reduction, n_seqs, row_weight, block_rows, bool(compact_ignored), row_index)
 
 
 @torch.no_grad()
-def sequence_nll(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, block_rows: int | None = None):
+def sequence_nll(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, block_rows: int | None = None,
+                 row_index: torch.Tensor | None = None):
     """Forward-only `get_batch_loss` (mm/trainer_utils.py:73-81; used by mm/eval.py:64-92): per-sequence
-    SUM of shifted token CE.  hidden [B, T, H], labels [B, T] (unshifted).  Returns fp32 [B]."""
-    b, t, h = hidden.shape
-    res = head_loss_fwd_bwd(hidden.reshape(b * t, h).to(torch.bfloat16).contiguous(),
+    SUM of shifted token CE.  hidden [B, T', H], labels [B, T] (unshifted); row_index: optional flat int32 [B * T] row map
+    into hidden.reshape(B * T', H) (T' > T: `remove_image_tokens`).  Returns fp32 [B]."""
+    b, tp, h = hidden.shape
+    res = head_loss_fwd_bwd(hidden.reshape(b * tp, h).to(torch.bfloat16).contiguous(),
                             weight.to(torch.bfloat16).contiguous(), KIND_CE, labels=shift_labels(labels),
                             reduction="seq_mean", n_seqs=b, need_dhidden=False, need_dweight=False,
-                            block_rows=block_rows, compact_ignored=True)
+                            block_rows=block_rows, compact_ignored=True, row_index=row_index)
     return res.seq_loss

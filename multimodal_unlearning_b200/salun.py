@@ -66,12 +66,19 @@ class FlatLayout:
 class SaliencyState:
     """The `gradients` dict of save_gradient_ratio as one flat bf16 buffer on the GPU."""
 
-    def __init__(self, layout: FlatLayout, device="cuda"):
+    def __init__(self, layout: FlatLayout, device="cuda", acc: torch.Tensor | None = None):
+        """acc: optional existing flat bf16 buffer in `layout` (e.g. a slice of another state's accumulator) to work on
+        in place instead of allocating a zeroed one."""
         self.layout = layout
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("SaliencyState lives on a CUDA device: SalUn masks have no CPU path here")
-        self.acc = torch.zeros(layout.total, dtype=torch.bfloat16, device=self.device)
+        if acc is None:
+            acc = torch.zeros(layout.total, dtype=torch.bfloat16, device=self.device)
+        elif (acc.dtype != torch.bfloat16 or not acc.is_cuda or acc.numel() != layout.total or not acc.is_contiguous()
+              or acc.data_ptr() % 16):
+            raise RuntimeError("SaliencyState: acc must be a contiguous, 16-byte aligned CUDA bf16 buffer of layout.total elements")
+        self.acc = acc
         self.seg_off, self.seg_numel, self.chunk_prefix = layout.device_tables(self.device)
         self.launches = 0
 
@@ -101,21 +108,66 @@ class SaliencyState:
             self.launches += 1
 
     # ---- generate_mask.py:47-85 -------------------------------------------------------------------
-    def select(self, thresholds: Sequence[float] = REFERENCE_THRESHOLDS) -> torch.Tensor:
-        """Per tensor and threshold: (bit pattern tau of the k-th largest key, ties to take, lo, hi) with
-        [lo, hi] the bf16 magnitude patterns whose key is tau, total = #{key == tau}).  int64 [S, n_th, 5]."""
-        lib = _lib.load()
+    def histogram(self) -> torch.Tensor:
+        """uint32 [S, 32768] (held as int32): per tensor, the number of elements whose fp16(|acc|) bit pattern is the bin."""
         lay = self.layout
         n_segs = len(lay.names)
         hist = torch.zeros((n_segs, N_BINS), dtype=torch.int32, device=self.device)
-        _lib.check(lib.clear_saliency_histogram(self.acc.data_ptr(), self.seg_off.data_ptr(), n_segs, lay.total,
-                                                hist.data_ptr(), _stream()), "clear_saliency_histogram")
+        _lib.check(_lib.load().clear_saliency_histogram(self.acc.data_ptr(), self.seg_off.data_ptr(), n_segs, lay.total,
+                                                        hist.data_ptr(), _stream()), "clear_saliency_histogram")
+        self.launches += 1
+        self.hist = hist
+        return hist
+
+    def hist_total(self, hist: torch.Tensor) -> torch.Tensor:
+        """int64 [32768]: the histogram of ALL tensors of this layout (zero padding excluded)."""
+        total = torch.empty(N_BINS, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.load().clear_saliency_hist_total(hist.data_ptr(), self.seg_off.data_ptr(), self.seg_numel.data_ptr(),
+                                                         len(self.layout.names), total.data_ptr(), _stream()),
+                   "clear_saliency_hist_total")
+        self.launches += 1
+        return total
+
+    def select_global(self, hist: torch.Tensor, total: torch.Tensor, n_total: int, thresholds: Sequence[float],
+                      rank_budget=None) -> torch.Tensor:
+        """Global-threshold records from the (possibly all-reduced) total histogram.  n_total: number of elements the
+        ranking runs over (all ranks).  rank_budget: optional callable (tau int64 [n_th], budget int64 [n_th]) -> int64
+        [n_th] giving the part of each tie budget that falls to THIS layout (ranks that own consecutive flat slices:
+        distributed.tie_budget_for_rank); None = the whole budget."""
+        lib = _lib.load()
+        n_th = len(thresholds)
+        tb = global_tau(total, n_total, thresholds)
+        override = None
+        if rank_budget is not None:
+            override = rank_budget(tb[:, 0], tb[:, 1]).to(torch.int64).contiguous()
+        n_segs = len(self.layout.names)
+        sel = torch.full((n_segs, n_th, 5), -1, dtype=torch.int64, device=self.device)
+        _lib.check(lib.clear_saliency_select_global_fill(hist.data_ptr(), self.seg_off.data_ptr(), self.seg_numel.data_ptr(),
+                                                         n_segs, tb.data_ptr(), override.data_ptr() if override is not None else None,
+                                                         n_th, sel.data_ptr(), _stream()), "clear_saliency_select_global_fill")
+        self.launches += 2
+        self.tau_budget = tb
+        return sel
+
+    def select(self, thresholds: Sequence[float] = REFERENCE_THRESHOLDS, scope: str = "per_tensor") -> torch.Tensor:
+        """Per tensor and threshold: (bit pattern tau of the k-th largest key, ties to take, lo, hi, total) with
+        [lo, hi] the bf16 magnitude patterns whose key is tau, total = #{key == tau}.  int64 [S, n_th, 5].
+        scope="per_tensor": k = int(th * numel) within each tensor — the shipped reference (generate_mask.py:54-85);
+        scope="global": ONE ranking over all tensors, k = int(th * total numel), ties by global flat index (upstream
+        SalUn's global rank, of which the reference's `start_index` is the vestige; SURVEY.md App. B #11)."""
+        lib = _lib.load()
+        lay = self.layout
+        n_segs = len(lay.names)
+        hist = self.histogram()
+        if scope == "global":
+            return self.select_global(hist, self.hist_total(hist), sum(lay.numels), thresholds)
+        if scope != "per_tensor":
+            raise ValueError(f"unknown scope {scope!r}: 'per_tensor' or 'global'")
         th = (C.c_double * len(thresholds))(*[float(t) for t in thresholds])
         sel = torch.full((n_segs, len(thresholds), 5), -1, dtype=torch.int64, device=self.device)
         _lib.check(lib.clear_saliency_select(hist.data_ptr(), self.seg_off.data_ptr(), self.seg_numel.data_ptr(), n_segs,
                                              th, len(thresholds), sel.data_ptr(), _stream()), "clear_saliency_select")
-        self.launches += 2
-        self.hist = hist
+        self.launches += 1
         return sel
 
     def mask_flat(self, sel: torch.Tensor, th_index: int, out: torch.Tensor | None = None,
@@ -135,22 +187,52 @@ class SaliencyState:
         self.launches += 3
         return out
 
-    def masks(self, thresholds: Sequence[float] = REFERENCE_THRESHOLDS) -> Iterator[tuple[float, dict]]:
+    def masks(self, thresholds: Sequence[float] = REFERENCE_THRESHOLDS, scope: str = "per_tensor") -> Iterator[tuple[float, dict]]:
         """Yields (threshold, {name: int8 mask of the parameter's shape}) — `process_threshold`'s hard_dict."""
-        sel = self.select(thresholds)
+        sel = self.select(thresholds, scope)
         for j, th in enumerate(thresholds):
             flat = self.mask_flat(sel, j)
             yield th, {n: self.layout.view(flat, i) for i, n in enumerate(self.layout.names)}
 
 
+def slice_layout(layout: FlatLayout, c0: int, c1: int) -> tuple[FlatLayout, int, int]:
+    """The mask chunks [c0, c1) of `layout` as a layout of their own: a contiguous range [f0, f1) of the flat buffer whose
+    segments are the PIECES of the tensors it intersects (a tensor cut by a slice boundary appears as one piece on either
+    side; chunks never straddle tensors, so every piece is a whole number of chunks of one tensor).  Returns
+    (piece layout, f0, f1); piece k of tensor `name` starting at element e is named "name@e"."""
+    chunk = int(_lib.load().clear_saliency_chunk_elems())
+    pieces, f0, f1 = [], None, None
+    for i, name in enumerate(layout.names):
+        a, b = max(c0, layout.chunk_prefix[i]), min(c1, layout.chunk_prefix[i + 1])
+        if a >= b:
+            continue
+        start = (a - layout.chunk_prefix[i]) * chunk
+        stop = min(layout.numels[i], (b - layout.chunk_prefix[i]) * chunk)
+        if f0 is None:
+            f0 = layout.offsets[i] + start
+        f1 = layout.offsets[i] + (stop + 7) // 8 * 8
+        pieces.append((f"{name}@{start}", (stop - start,)))
+    sub = FlatLayout(pieces)
+    if f0 is None:
+        return sub, 0, 0
+    assert sub.total == f1 - f0, "pieces of a chunk range are contiguous in the flat buffer"
+    return sub, f0, f1
+
+
 def sharded_masks(state: SaliencyState, thresholds: Sequence[float] = REFERENCE_THRESHOLDS, group=None,
-                  reduce_acc: bool = True) -> list[torch.Tensor]:
+                  reduce_acc: bool = True, scope: str = "per_tensor") -> list[torch.Tensor]:
     """Data-parallel mask generation.  The reference sums SIGNED gradients over all forget batches
     before taking |.| (generate_mask.py:44 then :49), so with the batches dealt out to ranks the accumulators are
-    all-reduced (sum, bf16) first.  Its thresholds are per tensor (:54-85): tensors are independent units — rank r
-    computes the masks of the tensors `distributed.partition_units` deals to it (no collective on that path) and the
-    bit-packed results are exchanged.  Returns one flat bit-packed mask per threshold in `state.layout`, identical on
-    every rank (feed `layout`-offset slices to MaskedAdamW, or `unpack_mask` them)."""
+    all-reduced (sum, bf16) first.  Returns one flat bit-packed mask per threshold in `state.layout`, identical on
+    every rank (feed `layout`-offset slices to MaskedAdamW, or `unpack_mask` them).
+
+    scope="per_tensor" (the shipped reference, :54-85): tensors are independent units — rank r computes the masks of the
+    tensors `distributed.partition_units` deals to it, no collective on that path; the packed results are merged by ONE
+    all-reduce per threshold (the ranks' bytes are disjoint).
+    scope="global" (upstream SalUn's global rank): rank r owns a contiguous 1/R slice of the flat buffer (whole mask
+    chunks); it histograms its slice, the 32768-bin totals are all-reduced over NCCL (256 KB), every rank derives the same
+    threshold key and tie budget, the budget is split over ranks by an exclusive prefix in slice (= flat index) order
+    (`distributed.tie_budget_for_rank`), each rank writes the mask of its slice, one all-gather per threshold."""
     import torch.distributed as dist
 
     from . import distributed as D
@@ -158,34 +240,82 @@ def sharded_masks(state: SaliencyState, thresholds: Sequence[float] = REFERENCE_
     lay = state.layout
     world = D.world_size()
     if world == 1:
-        sel = state.select(thresholds)
+        sel = state.select(thresholds, scope)
         return [state.mask_flat(sel, j, packed=True) for j in range(len(thresholds))]
+    if scope not in ("per_tensor", "global"):
+        raise ValueError(f"unknown scope {scope!r}: 'per_tensor' or 'global'")
     rank = dist.get_rank(group)
     if reduce_acc:
         dist.all_reduce(state.acc, op=dist.ReduceOp.SUM, group=group)
+    dev = state.device
+    n_th = len(thresholds)
+
+    if scope == "global":
+        ranges = D.partition_range(lay.n_chunks, world)
+        subs = [slice_layout(lay, *ranges[r]) for r in range(world)]
+        mine, f0, f1 = subs[rank]
+        sub = hist = None
+        local_total = torch.zeros(N_BINS, dtype=torch.int64, device=dev)
+        if mine.total:
+            sub = SaliencyState(mine, dev, acc=state.acc[f0:f1])
+            hist = sub.histogram()
+            local_total = sub.hist_total(hist)
+        total = D.reduce_histogram_(local_total.clone(), group)          # the NCCL histogram reduction (256 KB)
+
+        def rank_budget(tau, budget):
+            local_ties = torch.where(tau >= 0, local_total[tau.clamp(min=0)], torch.zeros_like(tau))
+            return D.tie_budget_for_rank(local_ties, budget, group)      # exclusive prefix over ranks = flat index order
+
+        if sub is not None:
+            sel = sub.select_global(hist, total, sum(lay.numels), thresholds, rank_budget)
+        else:  # a rank without a slice still takes part in the collectives
+            tb = global_tau(total, sum(lay.numels), thresholds)
+            rank_budget(tb[:, 0], tb[:, 1])
+        width = max((b - a) // 8 for _, a, b in subs)
+        out = []
+        for t in range(n_th):
+            send = torch.zeros(width, dtype=torch.uint8, device=dev)
+            if sub is not None:
+                sub.mask_flat(sel, t, out=send[: mine.total // 8], packed=True)
+            recv = torch.empty(world * width, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(recv, send, group=group)
+            full = torch.zeros(lay.total // 8, dtype=torch.uint8, device=dev)
+            for r, (_, a, b) in enumerate(subs):
+                if b > a:
+                    full[a // 8: b // 8].copy_(recv[r * width: r * width + (b - a) // 8])
+            out.append(full)
+        state.launches += (sub.launches if sub is not None else 0)
+        return out
+
     units = D.partition_units(lay.numels, world)
-    sub_layouts = [FlatLayout([(lay.names[i], lay.shapes[i]) for i in units[r]]) for r in range(world)]
-    mine = sub_layouts[rank]
-    sub = SaliencyState(mine, state.device)
+    mine = FlatLayout([(lay.names[i], lay.shapes[i]) for i in units[rank]])
+    sub = SaliencyState(mine, dev)
     for j, i in enumerate(units[rank]):
         n = lay.numels[i]
         sub.acc[mine.offsets[j]: mine.offsets[j] + n].copy_(state.acc[lay.offsets[i]: lay.offsets[i] + n])
     sel = sub.select(thresholds) if units[rank] else None
     out = []
-    for t in range(len(thresholds)):
-        full = torch.zeros(lay.total // 8, dtype=torch.uint8, device=state.device)
-        for r in range(world):
-            lr = sub_layouts[r]
-            if lr.total == 0:
-                continue
-            buf = sub.mask_flat(sel, t, packed=True) if r == rank else torch.empty(lr.total // 8, dtype=torch.uint8, device=state.device)
-            dist.broadcast(buf, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
-            for j, i in enumerate(units[r]):
+    for t in range(n_th):
+        full = torch.zeros(lay.total // 8, dtype=torch.uint8, device=dev)
+        if units[rank]:
+            buf = sub.mask_flat(sel, t, packed=True)
+            for j, i in enumerate(units[rank]):
                 nb = (lay.numels[i] + 7) // 8
-                full[lay.offsets[i] // 8: lay.offsets[i] // 8 + nb].copy_(buf[lr.offsets[j] // 8: lr.offsets[j] // 8 + nb])
+                full[lay.offsets[i] // 8: lay.offsets[i] // 8 + nb].copy_(buf[mine.offsets[j] // 8: mine.offsets[j] // 8 + nb])
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)         # disjoint bytes: the sum is the union
         out.append(full)
-    state.launches += 3 * len(thresholds) + 2
+    state.launches += sub.launches
     return out
+
+
+def global_tau(total: torch.Tensor, n_total: int, thresholds: Sequence[float]) -> torch.Tensor:
+    """int64 [n_th, 2] = (threshold key tau or -1, tie budget) of the global ranking, from the total histogram."""
+    n_th = len(thresholds)
+    th = (C.c_double * n_th)(*[float(t) for t in thresholds])
+    tb = torch.empty((n_th, 2), dtype=torch.int64, device=total.device)
+    _lib.check(_lib.load().clear_saliency_select_global_tau(total.data_ptr(), int(n_total), th, n_th, tb.data_ptr(), _stream()),
+               "clear_saliency_select_global_tau")
+    return tb
 
 
 def pack_mask(mask: torch.Tensor) -> torch.Tensor:
@@ -236,7 +366,8 @@ def save_gradient_ratio(forget_loader: Iterable, model: torch.nn.Module, criteri
         loss.backward()
         state.accumulate_model(model)
     os.makedirs(cfg.save_dir, exist_ok=True)
-    for th, hard_dict in state.masks(REFERENCE_THRESHOLDS):
+    scope = getattr(cfg, "scope", "per_tensor")  # extension: "global" = one ranking over all tensors (upstream SalUn)
+    for th, hard_dict in state.masks(REFERENCE_THRESHOLDS, scope):
         torch.save({k: v.cpu() for k, v in hard_dict.items()}, os.path.join(cfg.save_dir, f"with_{th}.pt"))
 
 

@@ -72,7 +72,12 @@ class _HeadCapture(nn.Module):
 
     def forward(self, x):
         self.hidden = x
-        return x[..., :1]
+        # The 1-wide placeholder depends on the weight (times zero): under DistributedDataParallel with
+        # find_unused_parameters=True — the reference's own setting, mm/forget.py — the reducer searches the graph of the
+        # wrapped forward's OUTPUTS for the parameters that will receive a gradient; lm_head.weight gets its gradient later,
+        # through the fused head, and must not be marked unused in the meantime.
+        w = self.__dict__["real"].weight
+        return x[..., :1] + (w.reshape(-1)[:1].sum() * 0).to(x.dtype)
 
 
 def _unwrap(model):
@@ -116,6 +121,25 @@ def trunk_hidden(model, model_inputs: dict):
     return cap.hidden, lm_head.weight
 
 
+def flat_row_index(idx: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """[B, L] per-sample row numbers (image_row_index) -> flat int32 [B * L] rows of hidden.reshape(B * n_rows, H): the
+    `row_index` input of the fused head."""
+    b = idx.shape[0]
+    return (idx + torch.arange(b, device=idx.device)[:, None] * n_rows).reshape(-1).to(torch.int32)
+
+
+def expand_labels(labels: torch.Tensor, input_ids: torch.Tensor, n_rows: int, image_token_id: int) -> torch.Tensor:
+    """Labels [B, L] -> [B, T'] when a legacy processor expanded the image placeholder inside the model (T' > L): every text
+    position keeps its label at its new row, the image rows (and the placeholder itself) are ignored — what HF's legacy
+    `_merge_input_ids_with_image_features` does to `labels` before its CE when the reference calls `model(**x).loss`."""
+    idx = image_row_index(input_ids, n_rows, image_token_id)
+    if idx is None:
+        return labels
+    keep = torch.where(input_ids == image_token_id, torch.full_like(labels, head.IGNORE_INDEX), labels)
+    out = torch.full((labels.shape[0], n_rows), head.IGNORE_INDEX, dtype=labels.dtype, device=labels.device)
+    return out.scatter(1, idx, keep)
+
+
 def image_row_index(input_ids: torch.Tensor, n_rows: int, image_token_id: int) -> torch.Tensor | None:
     """`remove_image_tokens` (mm/trainer_utils.py:48-70) as a row map: for each sample the indices of
     the L output rows that line up with the L input positions when the model expanded one image
@@ -143,6 +167,7 @@ class _Recipes:
         self._fwd, self._tfwd, self.beta, self.loss_args, self.block_rows = fwd, tfwd, beta, loss_args, block_rows
         self.kl_tag = kl_tag  # "kl" (mm, lower-cased names) or "KL" (nlp)
         self._cache, self._tcache = {}, {}
+        self.expand = lambda split, labels, n_rows: labels   # mm: expand_labels for legacy processors (T' > L)
 
     # One trunk forward per (model, split) and step: `scrub` reads both .logits and .loss of the same
     # retain forward (mm/trainer.py:244-257), `dpo` scores the same forwards twice.
@@ -159,12 +184,14 @@ class _Recipes:
     # -- building blocks -------------------------------------------------------------------------
     def ce(self, split, coef=1.0):
         """`model(**split).loss` — HF causal-LM CE, mean over non-ignored shifted labels (A2)."""
-        h, w, labels = self.fwd(split)
+        h, w, labels, _ = self.fwd(split)
+        if labels.shape[1] != h.shape[1]:   # legacy processor: image placeholder expanded inside the model
+            labels = self.expand(split, labels, h.shape[1])
         return head.fused_head_loss(h, w, KIND_CE, labels=head.shift_labels(labels), coef=coef,
                                     block_rows=self.block_rows, compact_ignored=True)
 
     def _with_teacher(self, split, kind, coef, beta=1.0):
-        h, w, _ = self.fwd(split)
+        h, w, _, _ = self.fwd(split)
         rh, rw = self.tfwd(split)
         if rh.shape != h.shape:
             raise RuntimeError(f"teacher and student produced different shapes on '{split}': {rh.shape} vs {h.shape}")
@@ -180,7 +207,7 @@ class _Recipes:
         return self._with_teacher(split, KIND_KL_REV, coef)
 
     def entropy(self, split, coef=1.0):
-        h, w, _ = self.fwd(split)
+        h, w, _, _ = self.fwd(split)
         return head.fused_head_loss(h, w, KIND_ENTROPY, coef=coef, block_rows=self.block_rows)
 
     def npo(self, split):
@@ -188,13 +215,14 @@ class _Recipes:
 
     def seq_ce(self, split, coef=1.0, row_weight=None):
         """get_batch_loss: per-sequence sums -> (mean over B scaled by coef, [B] sums) (A6c)."""
-        h, w, labels = self.fwd(split)
+        h, w, labels, rows = self.fwd(split)
         return head.fused_head_loss(h, w, KIND_CE, labels=head.shift_labels(labels), coef=coef, reduction="seq_mean",
-                                    n_seqs=h.shape[0], row_weight=row_weight, block_rows=self.block_rows, compact_ignored=True)
+                                    n_seqs=h.shape[0], row_weight=row_weight, block_rows=self.block_rows, compact_ignored=True,
+                                    row_index=rows)
 
-    def teacher_seq_logp(self, split, labels):
+    def teacher_seq_logp(self, split, labels, rows=None):
         rh, rw = self.tfwd(split)
-        return -head.sequence_nll(rh, rw, labels, block_rows=self.block_rows)
+        return -head.sequence_nll(rh, rw, labels, block_rows=self.block_rows, row_index=rows)
 
     # -- dispatch ----------------------------------------------------------------------------------
     def grad_diff(self, t):
@@ -219,22 +247,22 @@ class _Recipes:
         """-mean_b logsigmoid(0.1 * ((lp_idk - lp_fgt) - (lp_idk_ref - lp_fgt_ref)))  (mm/trainer.py:390-394).
         Two-phase: forward-only per-sequence log-probs fix the per-sequence weights, then the
         forward+backward runs with those weights on the rows."""
-        hi, wi, li = self.fwd("idk")
-        hf, wf, lf = self.fwd("forget")
+        hi, wi, li, ri = self.fwd("idk")
+        hf, wf, lf, rf = self.fwd("forget")
         with torch.no_grad():
-            pi = (-head.sequence_nll(hi.detach(), wi.detach(), li, self.block_rows)
-                  + head.sequence_nll(hf.detach(), wf.detach(), lf, self.block_rows))
-            ref = self.teacher_seq_logp("idk", li) - self.teacher_seq_logp("forget", lf)
+            pi = (-head.sequence_nll(hi.detach(), wi.detach(), li, self.block_rows, row_index=ri)
+                  + head.sequence_nll(hf.detach(), wf.detach(), lf, self.block_rows, row_index=rf))
+            ref = self.teacher_seq_logp("idk", li, ri) - self.teacher_seq_logp("forget", lf, rf)
             x = DPO_BETA * (pi - ref)
             wgt = DPO_BETA * torch.sigmoid(-x)  # -d logsigmoid(x)/dx = -sigmoid(-x): +w on idk CE rows, -w on forget CE rows
             value = -torch.nn.functional.logsigmoid(x).mean()
 
-        def weighted(h, w, labels, coef):
+        def weighted(h, w, labels, rows, coef):
             return head.fused_head_loss(h, w, KIND_CE, labels=head.shift_labels(labels), coef=coef, reduction="seq_mean",
-                                        n_seqs=h.shape[0], row_weight=wgt.repeat_interleave(h.shape[1]),
-                                        block_rows=self.block_rows, compact_ignored=True)[0]
+                                        n_seqs=h.shape[0], row_weight=wgt.repeat_interleave(labels.shape[1]),
+                                        block_rows=self.block_rows, compact_ignored=True, row_index=rows)[0]
 
-        surrogate = weighted(hi, wi, li, 1.0) + weighted(hf, wf, lf, -1.0)  # gradient of the true loss
+        surrogate = weighted(hi, wi, li, ri, 1.0) + weighted(hf, wf, lf, rf, -1.0)  # gradient of the true loss
         return surrogate + (value - surrogate).detach()
 
 
@@ -260,7 +288,9 @@ def enable_fused_head_allreduce(model, group=None):
     if not names:
         raise RuntimeError("lm_head.weight is not a parameter of the model")
     DDP._set_params_and_buffers_to_ignore_for_model(model, names)
-    reducer = D.FusedGradReducer(tuple(lm_head.weight.shape), lm_head.weight.device, group=group, average=True)
+    # 8 rotating buffers (2.1 GB at V x H = 32064 x 4096): recipes with up to six head invocations per step (sku: 5) keep every
+    # reduced gradient in place until backward, none is copied
+    reducer = D.FusedGradReducer(tuple(lm_head.weight.shape), lm_head.weight.device, group=group, average=True, n_buffers=8)
     head.set_dweight_reducer(reducer)
     return reducer
 
@@ -338,21 +368,20 @@ class MMTrainerForgetting(_TrainerBase):
         cfg = _unwrap(model).config
         image_token = getattr(cfg, "image_token_index", getattr(cfg, "image_token_id", None))
 
-        def rows(hidden, split):
+        # `remove_image_tokens` (mm/trainer_utils.py:48-70; the reference applies it in `dpo` only, mm/trainer.py:373-387): with
+        # a legacy processor the model expands the image placeholder into patch rows (T' > L).  No copy is made: the L rows
+        # that line up with the input positions are named by a row map that the fused head takes as a kernel input.
+        def row_map(hidden, split):
             ids = splits[split]["input_ids"]
             if image_token is None or hidden.shape[1] == ids.shape[1]:
-                return hidden
-            idx = image_row_index(ids, hidden.shape[1], image_token)
-            return torch.gather(hidden, 1, idx[..., None].expand(-1, -1, hidden.shape[-1]))
+                return None
+            return flat_row_index(image_row_index(ids, hidden.shape[1], image_token), hidden.shape[1])
 
-        # CE/KL/NPO/entropy consume every output row (the reference applies remove_image_tokens only
-        # in `dpo`); with a legacy processor the labels would not line up for CE there either — HF
-        # handles that inside the model, so only the dpo path needs the row map.
+        # KL / NPO / entropy consume every output row, as in the reference; CE terms see the labels the way HF's legacy merge
+        # hands them to its CE (expand_labels); `dpo` scores the cropped rows (crop=True).
         def fwd(split, crop=False):
             h, w = trunk_hidden(model, splits[split])
-            if crop:
-                h = rows(h, split)
-            return h, w, splits[split]["labels"]
+            return h, w, splits[split]["labels"], (row_map(h, split) if crop else None)
 
         def tfwd(split, crop=False):
             if teacher is None:
@@ -360,20 +389,20 @@ class MMTrainerForgetting(_TrainerBase):
             cache = _teacher_cache(self)
             keys = None
             if cache is not None:
-                keys = TeacherCache.sample_keys(splits[split], image_token, tag="crop" if crop else "")
+                keys = TeacherCache.sample_keys(splits[split], image_token)
                 h = cache.lookup(keys)
                 if h is not None:
                     return h.to(device), _locate_head(teacher)[2].weight.to(device)
             with torch.no_grad():
                 h, w = trunk_hidden(teacher, MMTrainerForgetting.to_device(next(teacher.parameters()).device, splits[split]))
-                if crop:
-                    h = rows(h, split)
             if cache is not None:
                 cache.store(keys, h)
             return h.to(device), w.to(device)
 
         r = _Recipes(fwd, tfwd, self.loss_beta, getattr(self, "loss_args", None) or {},
                      getattr(self, "block_rows", None), "kl")
+        if image_token is not None:
+            r.expand = lambda split, labels, n_rows: expand_labels(labels, splits[split]["input_ids"], n_rows, image_token)
         t = self.loss_type
         if t == "retain_ft":
             loss = r.ce("retain")
@@ -448,14 +477,15 @@ class CustomTrainerForgetting(_TrainerBase):
                   "retain": CustomTrainerForgetting.to_device(device, retain_inputs)}
         if idk_inputs:
             splits["idk"] = CustomTrainerForgetting.to_device(device, idk_inputs[0])
-        # nlp `idk`: one forward over cat(forget, retain), one mean (nlp/dataloader.py:403-410)
-        splits["forget+retain"] = tuple(torch.cat((a, b), dim=0) for a, b in zip(splits["forget"], splits["retain"]))
         teacher = getattr(self, "oracle_model", None)
 
         def fwd(split):
+            if split == "forget+retain" and split not in splits:
+                # nlp `idk`: one forward over cat(forget, retain), one mean (nlp/dataloader.py:403-410); built on demand
+                splits[split] = tuple(torch.cat((a, b), dim=0) for a, b in zip(splits["forget"], splits["retain"]))
             ids, labels, att = splits[split]
             h, w = trunk_hidden(model, {"input_ids": ids, "attention_mask": att})
-            return h, w, labels
+            return h, w, labels, None
 
         def tfwd(split):
             if teacher is None:

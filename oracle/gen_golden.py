@@ -10,6 +10,8 @@ Head fixtures (one file per loss type and trainer):
     the hidden states [B, T, 128] and labels, per teacher forward the hidden states, the loss, dH per
     student forward, and probes of dW (selected rows, column sums, squared norm).  lm_head weights are
     regenerated from seeds (oracle.ref_harness.head_weight); their checksums are stored.
+Row-map fixture (row_map.npz): the reference's `remove_image_tokens` + `get_batch_loss` on a synthetic legacy-processor
+    batch (T' = L + 575), see gen_row_map.
 SalUn fixture:
     reference `save_gradient_ratio` on a 2-layer Llama (hidden 32, vocab 512): per-batch gradients (bf16
     bit patterns), and the ten masks, from the unmodified code and from the same code with
@@ -232,9 +234,48 @@ def gen_regulariser():
     print("regulariser:", {k: float(v) for k, v in out.items() if "loss" in k})
 
 
+def gen_row_map():
+    """Legacy-processor case of `dpo` (mm/trainer.py:373-387): the model expands ONE image placeholder per sample into 576
+    patch rows (T' = L + 575), `remove_image_tokens` (mm/trainer_utils.py:48-70) crops the logits back to L rows and
+    `get_batch_loss` (:73-81) scores them.  Transformers 5.x pre-expands the placeholders, so the tiny-LLaVA fixtures never
+    take this branch; here the reference's two functions run, unmodified, on logits formed from stored hidden states:
+    inputs (hidden [B, T', H] bf16 bits, W [V, H] bf16 bits, input_ids, labels) and their outputs (the row of `logits` each
+    output row came from — recovered by tagging, the per-sequence losses, and d(sum of losses)/d hidden)."""
+    _, MMU, _, _ = RH.import_reference()
+    b, l, h, v, img_tok, n_patch = 4, 48, 64, 1000, 999, 576
+    tp = l + n_patch - 1
+    g = torch.Generator().manual_seed(11)
+    ids = torch.randint(0, 900, (b, l), generator=g)
+    starts = [5, 0, None, 30]                      # image first-occurrence index; sample 2 has no image (left padding)
+    for i, s0 in enumerate(starts):
+        if s0 is not None:
+            ids[i, s0] = img_tok
+    labels = torch.randint(0, v, (b, l), generator=g)
+    labels[:, :34] = -100                          # question / image part ignored
+    labels[1, 40:] = -100
+    hidden = torch.randn(b, tp, h, generator=g).to(torch.bfloat16)
+    w = (0.1 * torch.randn(v, h, generator=g)).to(torch.bfloat16)
+    hid = hidden.float().requires_grad_(True)
+    exact = torch.nn.functional.linear(hid, w.float())
+    logits = exact + (exact.to(torch.bfloat16).float() - exact).detach()   # a bf16 lm_head's output, straight-through
+    cropped = MMU.remove_image_tokens(ids, logits, img_tok)
+    loss = MMU.get_batch_loss(cropped, labels)
+    loss.sum().backward()
+    # which row of `logits` each cropped row is: crop a tensor of row numbers with the same function
+    tag = torch.arange(tp, dtype=torch.float32)[None, :, None].expand(b, tp, 1).contiguous()
+    rows = MMU.remove_image_tokens(ids, tag, img_tok)[..., 0].long()
+    np.savez_compressed(GOLDEN / "row_map.npz", input_ids=ids.numpy(), labels=labels.numpy(),
+                        hidden_bits=hidden.view(torch.int16).numpy(), weight_bits=w.view(torch.int16).numpy(),
+                        image_token=np.int64(img_tok), rows=rows.numpy(), seq_loss=loss.detach().double().numpy(),
+                        dhidden=hid.grad.float().numpy())
+    print("row_map: seq_loss", loss.detach().tolist())
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = set(sys.argv[1:]) or {"mm", "nlp", "salun", "reg"}
+    which = set(sys.argv[1:]) or {"mm", "nlp", "salun", "reg", "row_map"}
+    if "row_map" in which:
+        gen_row_map()
     if "reg" in which:
         gen_regulariser()
     if "mm" in which:

@@ -85,3 +85,50 @@ def test_two_rank_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _ddp_capture_worker(rank, world, port, out_dir):
+    """DistributedDataParallel(find_unused_parameters=True) — the reference's setting (mm/forget.py) — around a model whose
+    lm_head is swapped for the capture module during the wrapped forward: lm_head.weight gets its gradient later, from a
+    loss formed OUTSIDE the wrapped forward (here: plain torch ops standing in for the fused head, which needs a GPU).
+    Two wrapped forwards per backward, as in every grad_diff / KL recipe.  Without the capture module's weight-dependent
+    placeholder, DDP marks the weight unused and its hook then raises "Expected to mark a variable ready only once"."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from multimodal_unlearning_b200 import distributed as D
+    from multimodal_unlearning_b200 import trainer as T
+    from oracle import head_oracle as HO
+    from oracle import ref_harness as RH
+    D.init_from_env("gloo")
+    model = RH.tiny_llama(0)
+    ddp = DDP(model, find_unused_parameters=True)
+    batches = [RH.nlp_triple(2, 24, 10 + rank), RH.nlp_triple(2, 24, 20 + rank)]
+    for step in range(2):                      # twice: the reducer must be re-armed correctly for the next iteration
+        ddp.zero_grad(set_to_none=True)
+        loss = 0.0
+        for ids, lab, att in batches:
+            h, w = T.trunk_hidden(ddp, {"input_ids": ids, "attention_mask": att})
+            assert h.requires_grad and w is model.lm_head.weight
+            loss = loss + HO.hf_causal_ce(torch.nn.functional.linear(h, w), lab)
+        loss.backward()
+        g = model.lm_head.weight.grad
+        assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+        both = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(both, g.contiguous())
+        assert torch.equal(both[0], both[1]), "DDP averaged lm_head.weight.grad over the ranks"
+    # the same gradient as the stock head under the same wrapper (mean over ranks of per-rank gradients)
+    ref = RH.tiny_llama(0)
+    dref = DDP(ref, find_unused_parameters=True)
+    loss = sum(dref(input_ids=ids, attention_mask=att, labels=lab).loss for ids, lab, att in batches)
+    loss.backward()
+    assert torch.allclose(model.lm_head.weight.grad, ref.lm_head.weight.grad, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(model.model.layers[0].mlp.up_proj.weight.grad, ref.model.layers[0].mlp.up_proj.weight.grad, rtol=1e-3, atol=1e-7)
+    (Path(out_dir) / f"ddp{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_capture_head_under_ddp_find_unused_parameters(tmp_path):
+    port = _free_port()
+    mp.spawn(_ddp_capture_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ddp0").exists() and (tmp_path / "ddp1").exists()

@@ -41,7 +41,7 @@ def _worker(rank, world, port, out_dir):
     # the same mean, fused into the contraction: reduce-scatter in the dW epilogue over NVLink + multicast all-gather
     fused = D.FusedGradReducer((v, h), dev, average=True)
     nccl_dw = res.dweight.clone()
-    for it in range(4):                                        # both buffers, a buffer reuse, and (last) the peer-store all-gather
+    for it in range(5):                                        # every rotating buffer, a buffer reuse, and (it == 3) the peer-store all-gather
         os.environ["CLEAR_NO_MULTICAST"] = "1" if it == 3 else "0"
         tgt = fused.begin()
         r2 = head.head_loss_fwd_bwd(hid[sl], wgt, KIND_KL_FWD, ref_hidden=ref[sl], ref_weight=wgt, dweight_target=tgt,
@@ -101,13 +101,13 @@ def _ddp_worker(rank, world, port, out_dir):
     inputs = [RH.nlp_triple(2, 64, 100 + rank), RH.nlp_triple(2, 64, 200 + rank), RH.nlp_triple(2, 64, 300 + rank)]
     fake = types.SimpleNamespace(loss_type="KL", oracle_model=teacher, loss_beta=1.0, l1_lambda=0.0, l0_lambda=0.0)
 
-    def run(fused):
+    def run(fused, find_unused=False):
         model = copy.deepcopy(base)
         model.train()
         reducer = T.enable_fused_head_allreduce(model) if fused else None
         assert (reducer is not None) == fused
-        ddp = DDP(model, device_ids=[rank])
-        loss = T.CustomTrainerForgetting.compute_loss(fake, ddp, inputs)
+        ddp = DDP(model, device_ids=[rank], find_unused_parameters=find_unused)
+        loss = T.CustomTrainerForgetting.compute_loss(fake, ddp, inputs)   # "KL": two wrapped forwards, one backward
         loss.backward()
         torch.cuda.synchronize()
         head.set_dweight_reducer(None)
@@ -118,6 +118,14 @@ def _ddp_worker(rank, world, port, out_dir):
     for n in want:
         rel = ((got[n] - want[n]).norm() / want[n].norm().clamp_min(1e-30)).item()
         assert rel < 3e-2, (n, rel)
+    # find_unused_parameters=True is the reference's own DDP setting (mm/forget.py); lm_head.weight receives its gradient
+    # from the fused head, outside the wrapped forward, and must still be seen as used (the capture module's placeholder
+    # output depends on it) — stock DDP reducer and fused head all-reduce alike
+    for fused in (False, True):
+        again = run(fused, find_unused=True)
+        for n in want:
+            rel = ((again[n] - want[n]).norm() / want[n].norm().clamp_min(1e-30)).item()
+            assert rel < 3e-2, ("find_unused_parameters", fused, n, rel)
     # and the fused gradient is identical on both ranks
     g = got["lm_head.weight"].contiguous()
     both = [torch.empty_like(g) for _ in range(world)]
@@ -171,6 +179,19 @@ def _salun_worker(rank, world, port, out_dir):
             nb = (layout.numels[i] + 7) // 8
             got = salun.unpack_mask(packed[t][layout.offsets[i] // 8: layout.offsets[i] // 8 + nb].clone(), s)
             assert np.array_equal(got.cpu().numpy(), want[th][n]), (th, n)
+    # global-threshold scope: flat 1/R slices (tensor "e" is cut between the two ranks), NCCL-reduced 32768-bin histogram,
+    # tie budget split by an exclusive prefix over ranks — equal to ONE stable ranking over the concatenation
+    ths_g = (0.0, 0.1, 0.37, 0.5, 0.9, 1.0)
+    packed = salun.sharded_masks(state, ths_g, reduce_acc=False, scope="global")
+    want = SO.masks_global(total, ths_g)
+    for t, th in enumerate(ths_g):
+        for i, (n, s) in enumerate(shapes):
+            nb = (layout.numels[i] + 7) // 8
+            got = salun.unpack_mask(packed[t][layout.offsets[i] // 8: layout.offsets[i] // 8 + nb].clone(), s)
+            assert np.array_equal(got.cpu().numpy(), want[th][n]), ("global", th, n, int((got.cpu().numpy() != want[th][n]).sum()))
+    both = [torch.empty_like(packed[2]) for _ in range(world)]
+    dist.all_gather(both, packed[2])
+    assert torch.equal(both[0], both[1])
     (Path(out_dir) / f"salun_ok{rank}").write_text("ok")
     dist.destroy_process_group()
 

@@ -63,6 +63,37 @@ def test_image_row_index_is_remove_image_tokens():
         assert torch.equal(got, MMU.remove_image_tokens(ids, logits, tok))
 
 
+def test_row_map_against_the_reference_fixture():
+    """tests/golden/row_map.npz: the rows the UNMODIFIED remove_image_tokens kept on a legacy-processor batch (T' = L + 575,
+    image first / in the middle / absent) are the rows image_row_index names; expand_labels puts every text label on its row
+    and ignores the image rows."""
+    import numpy as np
+
+    from multimodal_unlearning_b200.trainer import expand_labels, flat_row_index, image_row_index
+    from tests._golden import GOLDEN
+    z = np.load(GOLDEN / "row_map.npz")
+    ids, labels, rows = torch.from_numpy(z["input_ids"]), torch.from_numpy(z["labels"]), torch.from_numpy(z["rows"])
+    tok = int(z["image_token"])
+    tp = z["hidden_bits"].shape[1]
+    idx = image_row_index(ids, tp, tok)
+    assert torch.equal(idx, rows)
+    flat = flat_row_index(idx, tp)
+    assert flat.dtype == torch.int32 and torch.equal(flat.view(ids.shape).long(), rows + torch.arange(ids.shape[0])[:, None] * tp)
+    exp = expand_labels(labels, ids, tp, tok)
+    assert exp.shape == (ids.shape[0], tp)
+    text = ids != tok
+    assert torch.equal(exp.gather(1, rows)[text], labels[text])
+    assert int((exp != -100).sum()) == int(((labels != -100) & text).sum())
+
+
+def test_partition_range_and_slice_layout():
+    from multimodal_unlearning_b200 import distributed as D
+    for n, w in ((10, 3), (2, 4), (0, 2), (823, 8)):
+        r = D.partition_range(n, w)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
 def test_loss_needs_teacher_is_case_insensitive():
     from multimodal_unlearning_b200.trainer import loss_needs_teacher
     for t in ("npo", "dpo", "scrub", "llmu", "sku", "KL", "kl", "grad_diff_forget_ce_retain_kl", "grad_diff_forget_KL_retain_ce"):
@@ -179,12 +210,16 @@ def test_head_loss_operator_is_registered_with_a_fake_kernel():
         h = torch.empty(64, 128, dtype=torch.bfloat16, device="cuda")
         w = torch.empty(1000, 128, dtype=torch.bfloat16, device="cuda")
         y = torch.empty(64, dtype=torch.int64, device="cuda")
-        loss, seq, dh, dw, rows = op(h, w, 0, y, None, None, None, None, 1.0, 1.0, "seq_mean", 4, 0, True, False, True)
+        loss, seq, dh, dw, rows = op(h, w, 0, y, None, None, None, None, 1.0, 1.0, "seq_mean", 4, 0, True, False, True, None)
         assert loss.shape == (1,) and seq.shape == (4,) and dh.shape == (64, 128) and dw.numel() == 0 and rows.shape == (64,)
         assert dh.dtype == torch.bfloat16 and loss.dtype == torch.float32
+        # with a row map: 32 evaluated rows out of the 64 rows of hidden; dH keeps hidden's shape
+        idx = torch.empty(32, dtype=torch.int32, device="cuda")
+        loss, seq, dh, dw, rows = op(h, w, 0, y[:32], None, None, None, None, 1.0, 1.0, "reference", 0, 0, True, True, False, idx)
+        assert dh.shape == (64, 128) and dw.shape == (1000, 128) and rows.shape == (32,)
     with pytest.raises(RuntimeError, match="CUDA"):
         op(torch.zeros(8, 16, dtype=torch.bfloat16), torch.zeros(32, 16, dtype=torch.bfloat16), 0, torch.zeros(8, dtype=torch.int64),
-           None, None, None, None, 1.0, 1.0, "reference", 0, 0, True, True, False)
+           None, None, None, None, 1.0, 1.0, "reference", 0, 0, True, True, False, None)
 
 
 def test_enable_fused_head_allreduce_without_a_process_group_is_a_no_op():
@@ -196,10 +231,9 @@ def test_enable_fused_head_allreduce_without_a_process_group_is_a_no_op():
     assert not getattr(model, "_ddp_params_and_buffers_to_ignore", [])
 
 
-def test_compaction_threshold_and_defaults():
+def test_operator_schema_and_defaults():
     from multimodal_unlearning_b200 import head
-    assert 0.5 < head.COMPACT_MAX_FRACTION < 1.0
-    assert head.DEFAULT_BLOCK_ROWS == 8192 and head.MAX_BF16_ACCUM_BLOCKS >= 1
-    # the operator schema carries the flag (bool, last argument)
+    assert head.DEFAULT_BLOCK_ROWS in (2048, 4096, 8192) and head.MAX_BF16_ACCUM_BLOCKS >= 1
+    # the operator schema carries the compaction flag and the row map
     schema = str(torch.ops.clear_b200.head_loss.default._schema)
-    assert "bool compact_ignored" in schema and "str reduction" in schema
+    assert "bool compact_ignored" in schema and "str reduction" in schema and "Tensor? row_index" in schema

@@ -207,3 +207,29 @@ def test_regulariser_oracle_matches_the_reference_compute_loss():
             sign = sign[:64] if sign.dim() == 2 else sign
             got_d = torch.from_numpy(z[k])
             assert torch.allclose(got_d, l1 * sign, atol=2e-6), (tag, name)   # fp32 gradient difference of two backward runs
+
+
+def test_global_scope_oracle_is_one_ranking_over_all_tensors():
+    """SO.masks_global (scope="global"; parity unpinned upstream, see its docstring): equals the pinned per-tensor rule applied
+    to the concatenation; popcount = int(th * total); nested in th; differs from the per-tensor masks when tensors have
+    different scales, coincides with them for a single tensor."""
+    g = torch.Generator().manual_seed(3)
+    named = {"a": (torch.randn(37, 11, generator=g) * 4).round().div(4).to(torch.bfloat16),          # ties
+             "b": (1e-3 * torch.randn(1000, generator=g)).to(torch.bfloat16),                         # small scale
+             "c": torch.zeros(13, dtype=torch.bfloat16), "d": torch.randn(5, generator=g).to(torch.bfloat16)}
+    ths = (0.0, 0.1, 0.5, 0.77, 1.0)
+    got = SO.masks_global(named, ths)
+    total = sum(v.numel() for v in named.values())
+    cat = np.concatenate([SO.saliency_keys(v) for v in named.values()])
+    prev = None
+    for th in ths:
+        flat = np.concatenate([got[th][n].reshape(-1) for n in named])
+        assert np.array_equal(flat, SO.mask_of_keys(cat, th))
+        assert int(flat.sum()) == int(th * total)
+        if prev is not None:
+            assert np.all(flat >= prev)
+        prev = flat
+    per = SO.masks(named, (0.5,))[0.5]
+    assert int(got[0.5]["b"].sum()) < int(per["b"].sum())            # the small-scale tensor loses under a global rank
+    one = {"a": named["a"]}
+    assert np.array_equal(SO.masks_global(one, (0.3,))[0.3]["a"], SO.masks(one, (0.3,))[0.3]["a"])

@@ -374,3 +374,58 @@ def test_full_llama7b_parameter_list_properties():
     assert int((mom != 0).sum().item()) == int(sel_nonzero.sum().item())
     del p, mom, var, moved, sel_nonzero, m50, bits, st
     torch.cuda.empty_cache()
+
+
+def _check_global(named, ths):
+    from multimodal_unlearning_b200 import salun
+    layout = salun.FlatLayout([(n, v.shape) for n, v in named.items()])
+    state = salun.SaliencyState(layout, "cuda:0")
+    state.accumulate_flat(_flat(layout, named, torch.bfloat16).cuda())
+    want = SO.masks_global(named, ths)
+    got = dict(state.masks(ths, scope="global"))
+    for th in ths:
+        for n in named:
+            g = got[th][n].cpu().numpy()
+            assert np.array_equal(g, want[th][n]), ("global", th, n, int((g != want[th][n]).sum()))
+    return state, layout
+
+
+def test_global_scope_bit_exact():
+    """scope="global": ONE ranking over all tensors (k = int(th * total), ties by global flat index) — bit-exact against the
+    oracle's stable sort of the concatenated keys.  Tensors of very different scales, heavy ties that straddle tensors,
+    exact zeros next to the zero padding between tensors, odd sizes, fp16 overflow, th = 0 and th = 1."""
+    g = torch.Generator().manual_seed(4)
+    named = {"a": (torch.randn(1000003, generator=g) * 4).round() / 4,        # heavy ties
+             "b": torch.randn(8, generator=g), "c": torch.randn(3, 5, generator=g),
+             "d": (torch.randn(2048, 1024, generator=g) * 4).round() / 4,     # the same tie values again, in a later tensor
+             "e": torch.randn(1, generator=g), "f": torch.randn(70001, generator=g) * 1e-9,   # flushes to fp16 zero
+             "z": torch.zeros(1003), "h": torch.randn(333, 77, generator=g) * 1e-3}
+    named["d"][:, ::3] = 0.0
+    named["d"][5, 7] = 1e6                                                    # overflows fp16 -> inf
+    named = {n: v.to(torch.bfloat16) for n, v in named.items()}
+    ths = (0.0, 0.05, 0.1, 0.25, 0.5, 0.75, 0.9, 0.999, 1.0)
+    state, layout = _check_global(named, ths)
+    # the reference's ten thresholds as well, and the bit-packed format
+    sel = state.select(SO.REFERENCE_THRESHOLDS, scope="global")
+    want = SO.masks_global(named, SO.REFERENCE_THRESHOLDS)
+    total = sum(layout.numels)
+    from multimodal_unlearning_b200 import salun
+    for j, th in enumerate(SO.REFERENCE_THRESHOLDS):
+        bits = state.mask_flat(sel, j, packed=True)
+        ones = 0
+        for i, n in enumerate(layout.names):
+            nb = (layout.numels[i] + 7) // 8
+            m = salun.unpack_mask(bits[layout.offsets[i] // 8: layout.offsets[i] // 8 + nb].clone(), layout.shapes[i]).cpu().numpy()
+            assert np.array_equal(m, want[th][n]), (th, n)
+            ones += int(m.sum())
+        assert ones == int(th * total)
+
+
+def test_global_scope_single_tensor_equals_per_tensor():
+    g = torch.Generator().manual_seed(5)
+    named = {"only": ((torch.randn(50000, generator=g) * 8).round() / 8).to(torch.bfloat16)}
+    state, _ = _check_global(named, (0.1, 0.5, 0.9))
+    per = dict(state.masks((0.1, 0.5, 0.9)))
+    glo = dict(state.masks((0.1, 0.5, 0.9), scope="global"))
+    for th in per:
+        assert torch.equal(per[th]["only"], glo[th]["only"])
