@@ -365,6 +365,36 @@ typedef struct ClearAdamWArgs {
 } ClearAdamWArgs;
 int clear_masked_adamw(const ClearAdamWArgs* args, void* stream);
 
+/* Masked AdamW with 8-bit block-wise states.  The reference trains with optim="adamw_bnb_8bit"
+ * (mm/forget.py:156, nlp/forget.py:166 -> bitsandbytes==0.43.3, absent here: PARITY UNPINNED; the oracle restates what this
+ * computes).  Both moments are one byte per parameter: an index into a 256-entry sorted codebook (code1 signed for exp_avg,
+ * code2 non-negative for exp_avg_sq; host-generated "dynamic" maps) times one fp32 absmax per block of
+ * clear_adamw8_block_elems() = 256 parameters (absmax1 / absmax2: ceil(n / 256) floats each).  One fused pass: dequantise ->
+ * the update of clear_masked_adamw (same operation order) -> new block absmax -> requantise; quantisation = #{fp32 midpoints of
+ * neighbouring code entries that are < x / absmax}.  qlut1 (65536 bytes) / qlut2 (32768 bytes): for every top-16-bit pattern of
+ * the order-preserving float key (qlut2: of the non-negative floats) a lower bound of that count (any lower bound is
+ * correct; a tight one is fast).  States start as the index of 0.0 with absmax 0. */
+typedef struct ClearAdamW8Args {
+  void* param;            /* bf16 [n] */
+  const void* grad;       /* bf16 [n] */
+  uint8_t* state1;        /* [n] code indices of exp_avg */
+  uint8_t* state2;        /* [n] code indices of exp_avg_sq */
+  float* absmax1;         /* [ceil(n / 256)] */
+  float* absmax2;
+  const float* code1;     /* device fp32 [256], ascending */
+  const float* code2;
+  const uint8_t* qlut1;   /* device uint8 [65536] */
+  const uint8_t* qlut2;   /* device uint8 [32768] */
+  const int8_t* mask;     /* optional int8 [n] ... */
+  const uint8_t* mask_bits; /* ... or bit-packed; both NULL = all ones */
+  int64_t n;
+  double lr, beta1, beta2, eps, weight_decay;
+  int32_t step;
+  const float* grad_scale_dev;
+} ClearAdamW8Args;
+int32_t clear_adamw8_block_elems(void);
+int clear_masked_adamw_8bit(const ClearAdamW8Args* args, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Whole-model reductions around the update (one pass over HBM each, bitwise reproducible).
  * partials: double workspace of clear_reduce_partials_elems() elements; out: device doubles;

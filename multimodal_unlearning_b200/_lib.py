@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     # ABI 3
     "clear_head_lse_partials_f32", "clear_rows_gather_dev", "clear_rows_scatter_dev", "clear_index_compose",
     "clear_saliency_hist_total", "clear_saliency_select_global_tau", "clear_saliency_select_global_fill",
+    "clear_adamw8_block_elems", "clear_masked_adamw_8bit",
 )
 ABI_VERSION = 3
 
@@ -92,6 +93,14 @@ class AdamWArgs(C.Structure):
                 ("mask_bits", C.c_void_p)]
 
 
+class AdamW8Args(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("state1", C.c_void_p), ("state2", C.c_void_p),
+                ("absmax1", C.c_void_p), ("absmax2", C.c_void_p), ("code1", C.c_void_p), ("code2", C.c_void_p),
+                ("qlut1", C.c_void_p), ("qlut2", C.c_void_p), ("mask", C.c_void_p), ("mask_bits", C.c_void_p), ("n", C.c_int64),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("step", C.c_int32), ("grad_scale_dev", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -152,6 +161,8 @@ def load() -> C.CDLL:
     lib.clear_saliency_select_global_tau.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p]
     lib.clear_saliency_select_global_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                                       C.c_void_p, C.c_void_p]
+    lib.clear_adamw8_block_elems.restype = C.c_int32
+    lib.clear_masked_adamw_8bit.argtypes = [C.POINTER(AdamW8Args), C.c_void_p]
     lib.clear_head_loss_workspace_bytes.argtypes = [C.POINTER(HeadArgs), C.POINTER(C.c_size_t)]
     lib.clear_head_loss_fwd_bwd.argtypes = [C.POINTER(HeadArgs), C.c_void_p, C.c_size_t, C.c_void_p]
     for name in EXPORTED_SYMBOLS:

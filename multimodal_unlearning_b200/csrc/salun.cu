@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "common.h"
+#include "adam_common.cuh"
 
 namespace clear {
 namespace {
@@ -683,30 +684,6 @@ __global__ void __launch_bounds__(kChunkThreads) tie_fix_kernel(const __nv_bfloa
 // ------------------------------------------------------------------------------------------------
 // masked AdamW
 // ------------------------------------------------------------------------------------------------
-struct AdamConsts {
-  float decay;      // 1 - lr * weight_decay
-  float w1;         // 1 - beta1
-  float beta2, w2;  // beta2, 1 - beta2
-  float bc2_sqrt;   // sqrt(1 - beta2^step)
-  float step_size;  // lr / (1 - beta1^step)
-  float eps;
-  const float* grad_scale;  // optional device scalar: clipping coefficient
-};
-
-__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamConsts& c) {
-  p = __fmul_rn(p, c.decay);                                        // param.mul_(1 - lr * wd)
-  m = __fadd_rn(m, __fmul_rn(c.w1, __fsub_rn(g, m)));               // exp_avg.lerp_(grad, 1 - beta1)
-  v = __fadd_rn(__fmul_rn(v, c.beta2), __fmul_rn(c.w2, __fmul_rn(g, g)));  // mul_(beta2).addcmul_(g, g, 1 - beta2)
-  // The IEEE square root / division take a slow path (a subroutine call, the whole warp with it) when an
-  // operand is zero — which every masked-out parameter is, forever.  A zero operand is swapped for 1 and
-  // the exact result (sqrt(+0) = +0, +-0 / d = +-0) selected afterwards: same bits, fast path.
-  const float sq = (v == 0.f) ? v : __fsqrt_rn((v == 0.f) ? 1.f : v);
-  const float sd = (sq == 0.f) ? sq : __fdiv_rn((sq == 0.f) ? 1.f : sq, c.bc2_sqrt);
-  const float denom = __fadd_rn(sd, c.eps);
-  const float q = (m == 0.f) ? __fmul_rn(m, 1.f) : __fdiv_rn((m == 0.f) ? 1.f : m, denom);
-  return __fsub_rn(p, __fmul_rn(c.step_size, q));   // addcdiv_(exp_avg, denom, -step_size)
-}
-
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): the eight fp32 moments of a thread's eight parameters are 32
 // contiguous bytes, so one instruction per warp covers 1 KB contiguously instead of two half-used 16-byte accesses at a
 // 32-byte stride.
@@ -982,18 +959,7 @@ int clear_masked_adamw(const ClearAdamWArgs* a, void* stream) {
     return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: the fp32 moments must be 32-byte aligned (256-bit accesses)");
   if (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)) return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw: mask must be 8-byte aligned");
   if (a->mask && a->mask_bits) return fail(CLEAR_ERR_KIND, "clear_masked_adamw: pass mask or mask_bits, not both");
-  // Scalar prologue of torch.optim.adam._single_tensor_adam, in double like the Python floats there.
-  AdamConsts c;
-  c.decay = (float)(1.0 - a->lr * a->weight_decay);
-  c.w1 = (float)(1.0 - a->beta1);
-  c.beta2 = (float)a->beta2;
-  c.w2 = (float)(1.0 - a->beta2);
-  const double bc1 = 1.0 - pow(a->beta1, (double)a->step);
-  const double bc2 = 1.0 - pow(a->beta2, (double)a->step);
-  c.step_size = (float)(a->lr / bc1);
-  c.bc2_sqrt = (float)sqrt(bc2);
-  c.eps = (float)a->eps;
-  c.grad_scale = a->grad_scale_dev;
+  const AdamConsts c = make_adam_consts(a->lr, a->beta1, a->beta2, a->eps, a->weight_decay, a->step, a->grad_scale_dev);
   if (a->mask_bits)
     adamw_kernel<true><<<stream_grid(a->n >> 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<__nv_bfloat16*>(a->param), static_cast<const __nv_bfloat16*>(a->grad), a->exp_avg, a->exp_avg_sq,

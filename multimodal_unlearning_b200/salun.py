@@ -371,14 +371,103 @@ def save_gradient_ratio(forget_loader: Iterable, model: torch.nn.Module, criteri
         torch.save({k: v.cpu() for k, v in hard_dict.items()}, os.path.join(cfg.save_dir, f"with_{th}.pt"))
 
 
+# --------------------------------------------------------------------------------------------------
+# 8-bit block-wise optimiser states (the reference trains with optim="adamw_bnb_8bit",
+# mm/forget.py:156 — bitsandbytes, absent here: parity unpinned, see csrc/adamw8.cu)
+# --------------------------------------------------------------------------------------------------
+ADAMW8_MIN_NUMEL = 4096   # smaller tensors (norm weights of tiny models, biases) keep fp32 moments, as bitsandbytes' min_8bit_size does
+
+
+def dynamic_codebook(signed: bool) -> torch.Tensor:
+    """256 sorted fp32 code values in [-1, 1] (signed: exp_avg) or [0, 1] (unsigned: exp_avg_sq) of the "dynamic" 8-bit data
+    type of block-wise 8-bit optimisers: seven decades 1e-6 .. 1, decade d holding 2^d (signed: per sign) / 2^(d+1) (unsigned)
+    values at the centres of equal cells of [0.1, 1] * 10^(d-6), plus 0 and 1 — fine resolution near full scale, seven
+    orders of magnitude of dynamic range below it."""
+    vals = [0.0, 1.0]
+    for d in range(7):
+        cells = 2 ** d if signed else 2 ** (d + 1)
+        edges = torch.linspace(0.1, 1.0, cells + 1, dtype=torch.float32)
+        centres = ((edges[:-1] + edges[1:]) / 2.0) * (10.0 ** (d - 6))
+        vals += centres.tolist()
+        if signed:
+            vals += (-centres).tolist()
+    code = torch.tensor(sorted(vals), dtype=torch.float32)
+    assert code.numel() == 256
+    return code
+
+
+def quantisation_tables(code: torch.Tensor, signed: bool) -> torch.Tensor:
+    """uint8 lower-bound table of the kernel's quantiser: for every top-16-bit pattern of the order-preserving float key
+    (signed: all 65536; unsigned: the 32768 non-negative ones) the number of code midpoints below the SMALLEST float with that
+    pattern — a lower bound of the index of any float of the bucket, which the kernel finishes by comparing midpoints."""
+    mid = ((code[:-1] + code[1:]) * 0.5).to(torch.float32)
+    if signed:
+        u = torch.arange(65536, dtype=torch.int64) << 16                       # smallest sortable key of the bucket
+        bits = torch.where(u >= 0x80000000, u ^ 0x80000000, (~u) & 0xFFFFFFFF)   # back to the IEEE pattern
+        # a negative float's bucket: its smallest member has all low key bits 0, i.e. all low pattern bits 1
+    else:
+        bits = torch.arange(32768, dtype=torch.int64) << 16
+    x = torch.where(bits >= 0x80000000, bits - (1 << 32), bits).to(torch.int32).view(torch.float32)
+    x = torch.nan_to_num(x, nan=-float("inf") if signed else 0.0)
+    return torch.searchsorted(mid, x.contiguous(), right=False).to(torch.uint8)
+
+
+class _Adam8Tables:
+    """Device copies of the two codebooks and their quantisation tables, one set per device."""
+
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, device):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in cls._cache:
+            c1, c2 = dynamic_codebook(True), dynamic_codebook(False)
+            cls._cache[key] = (c1.to(device), c2.to(device), quantisation_tables(c1, True).to(device), quantisation_tables(c2, False).to(device),
+                               int(torch.nonzero(c1 == 0)[0]), int(torch.nonzero(c2 == 0)[0]))
+        return cls._cache[key]
+
+
+def masked_adamw8_flat(param: torch.Tensor, grad: torch.Tensor, state1: torch.Tensor, state2: torch.Tensor, absmax1: torch.Tensor,
+                       absmax2: torch.Tensor, mask: torch.Tensor | None, step: int, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
+                       weight_decay=0.01, grad_scale: torch.Tensor | None = None) -> None:
+    """One launch of the 8-bit-state masked AdamW over a flat bf16 parameter buffer.  state1 / state2: uint8 [n] code indices
+    (start: adamw8_init); absmax1 / absmax2: fp32 [ceil(n / 256)]."""
+    c1, c2, q1, q2, _, _ = _Adam8Tables.get(param.device)
+    bits = mask if (mask is not None and mask.dtype == torch.uint8) else None
+    if bits is not None:
+        mask = None
+    a = _lib.AdamW8Args(param=param.data_ptr(), grad=grad.data_ptr(), state1=state1.data_ptr(), state2=state2.data_ptr(),
+                        absmax1=absmax1.data_ptr(), absmax2=absmax2.data_ptr(), code1=c1.data_ptr(), code2=c2.data_ptr(),
+                        qlut1=q1.data_ptr(), qlut2=q2.data_ptr(), mask=mask.data_ptr() if mask is not None else None,
+                        mask_bits=bits.data_ptr() if bits is not None else None, n=param.numel(), lr=lr, beta1=betas[0], beta2=betas[1],
+                        eps=eps, weight_decay=weight_decay, step=step,
+                        grad_scale_dev=grad_scale.data_ptr() if grad_scale is not None else None)
+    _lib.check(_lib.load().clear_masked_adamw_8bit(C.byref(a), _stream()), "clear_masked_adamw_8bit")
+
+
+def adamw8_init(n: int, device) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(state1, state2, absmax1, absmax2) of n parameters at step 0: both moments exactly zero."""
+    device = torch.device(device)
+    _, _, _, _, z1, z2 = _Adam8Tables.get(device)
+    nb = (n + 255) // 256
+    return (torch.full((n,), z1, dtype=torch.uint8, device=device), torch.full((n,), z2, dtype=torch.uint8, device=device),
+            torch.zeros(nb, dtype=torch.float32, device=device), torch.zeros(nb, dtype=torch.float32, device=device))
+
+
 class MaskedAdamW(torch.optim.Optimizer):
     """AdamW whose gradient is multiplied by a SalUn mask first (upstream SalUn: `param.grad *= mask[name]`
     before `optimizer.step()`).  bf16 parameters and gradients, fp32 moments, torch's
     `_single_tensor_adam` operation order; one fused pass over 23 bytes per parameter."""
 
     def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, masks: dict | None = None,
-                 max_grad_norm: float | None = None):
+                 max_grad_norm: float | None = None, state_bits: int = 32):
+        """state_bits=8: block-wise 8-bit moments (2 bytes of optimiser state per parameter instead of 8; the scheme of the
+        `adamw_bnb_8bit` optimiser the reference trains with, mm/forget.py:156) for tensors of at least ADAMW8_MIN_NUMEL
+        elements; 32 (default): fp32 moments, bit-exact with torch.optim.AdamW's operation order."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if state_bits not in (8, 32):
+            raise ValueError("state_bits must be 8 or 32")
+        self.state_bits = state_bits
         self.masks = masks or {}  # param -> int8 tensor
         # Global gradient-norm clipping fused into the update (HF Trainer's default max_grad_norm = 1.0 applies to
         # the reference runs: the override is commented out at mm/forget.py:151).  The norm is taken over the MASKED
@@ -429,13 +518,22 @@ class MaskedAdamW(torch.optim.Optimizer):
                 if p.dtype != torch.bfloat16 or not p.is_cuda or not p.is_contiguous():
                     raise RuntimeError("MaskedAdamW updates contiguous CUDA bf16 parameters")
                 st = self.state[p]
+                eight = self.state_bits == 8 and p.numel() >= ADAMW8_MIN_NUMEL
                 if not st:
                     st["step"] = 0
-                    st["exp_avg"] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
-                    st["exp_avg_sq"] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+                    if eight:
+                        st["state1"], st["state2"], st["absmax1"], st["absmax2"] = adamw8_init(p.numel(), p.device)
+                    else:
+                        st["exp_avg"] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+                        st["exp_avg_sq"] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
                 st["step"] += 1
                 g = p.grad.to(torch.bfloat16).contiguous()
                 m = self.masks.get(p)
+                if eight:
+                    masked_adamw8_flat(p.view(-1), g.view(-1), st["state1"], st["state2"], st["absmax1"], st["absmax2"], m,
+                                       st["step"], lr=group["lr"], betas=(b1, b2), eps=group["eps"],
+                                       weight_decay=group["weight_decay"], grad_scale=scale)
+                    continue
                 bits = m if (m is not None and m.dtype == torch.uint8) else None
                 if bits is not None:
                     m = None

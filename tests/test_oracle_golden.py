@@ -233,3 +233,32 @@ def test_global_scope_oracle_is_one_ranking_over_all_tensors():
     assert int(got[0.5]["b"].sum()) < int(per["b"].sum())            # the small-scale tensor loses under a global rank
     one = {"a": named["a"]}
     assert np.array_equal(SO.masks_global(one, (0.3,))[0.3]["a"], SO.masks(one, (0.3,))[0.3]["a"])
+
+
+def test_adamw8_oracle_properties():
+    """8-bit block-wise states (parity unpinned upstream: bitsandbytes is absent).  The oracle's restatement is internally
+    consistent: codebooks sorted with 0 and 1; quantising exactly representable values (code * absmax) is the identity on the
+    indices (idempotence of dequantise -> quantise); one 8-bit step stays close to the fp32-state step it approximates."""
+    for signed in (True, False):
+        code = SO.dynamic_map(signed)
+        assert code.size == 256 and np.all(np.diff(code) > 0) and code[-1] == 1.0 and (code[0] == 0.0) != signed
+    c1 = SO.dynamic_map(True)
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, 256, 1024).astype(np.uint8)
+    idx[::256] = 255                                             # every block holds its absmax exactly (code 1.0)
+    absmax = np.asarray([0.5, 3.0, 1e-4, 7.0], np.float32)
+    x = (c1[idx] * np.repeat(absmax, 256)).astype(np.float32)
+    q, a = SO.adamw8_quantise(x, c1)
+    assert np.array_equal(a, absmax) and np.array_equal(q, idx)
+    n = 2048
+    g = torch.Generator().manual_seed(1)
+    p = torch.randn(n, generator=g).to(torch.bfloat16)
+    gr = (0.01 * torch.randn(n, generator=g)).to(torch.bfloat16)
+    z1 = int(np.nonzero(c1 == 0)[0][0])
+    s1, s2 = np.full(n, z1, np.uint8), np.zeros(n, np.uint8)
+    a1, a2 = np.zeros(8, np.float32), np.zeros(8, np.float32)
+    p8, s1, s2, a1, a2 = SO.adamw8_step(p, gr, s1, s2, a1, a2, None, 1, lr=1e-3)
+    p32, m, v = SO.adamw_step(p, gr, np.zeros(n, np.float32), np.zeros(n, np.float32), None, 1, lr=1e-3)
+    assert torch.equal(p8, p32)                                   # the states are quantised AFTER the update: step 1 is exact
+    m8 = SO.dynamic_map(True)[s1] * np.repeat(a1, 256)
+    assert np.abs(m8 - m).max() <= 0.02 * np.abs(m).max()

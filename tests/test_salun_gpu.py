@@ -429,3 +429,90 @@ def test_global_scope_single_tensor_equals_per_tensor():
     glo = dict(state.masks((0.1, 0.5, 0.9), scope="global"))
     for th in per:
         assert torch.equal(per[th]["only"], glo[th]["only"])
+
+
+# --------------------------------------------------------------------------------------------------
+# 8-bit block-wise optimiser states — parity unpinned upstream (bitsandbytes absent): bit-exact against
+# the oracle's restatement of the scheme, and bounded against the fp32-state update
+# --------------------------------------------------------------------------------------------------
+def test_adamw8_codebooks():
+    from multimodal_unlearning_b200 import salun
+    for signed in (True, False):
+        code = salun.dynamic_codebook(signed).numpy()
+        want = SO.dynamic_map(signed)
+        assert code.shape == (256,) and np.all(np.diff(code) > 0) and code[-1] == 1.0
+        assert (code.min() == 0.0) != signed and np.count_nonzero(code == 0.0) == 1
+        # same published construction; linspace arithmetic (torch fp32 vs numpy) may differ in the last bit
+        assert np.max(np.abs(code - want) / np.maximum(np.abs(want), 1e-30)) <= 2e-7
+        lut = salun.quantisation_tables(torch.from_numpy(code), signed)
+        assert lut.numel() == (65536 if signed else 32768) and lut.dtype == torch.uint8
+
+
+@pytest.mark.parametrize("n", [4096, 70001, 256 * 300 + 8])
+@pytest.mark.parametrize("mask_kind", ["none", "int8", "bits"])
+def test_adamw8_bit_exact_vs_oracle(n, mask_kind):
+    """Several steps of clear_masked_adamw_8bit against oracle.adamw8_step: parameters (bf16 bits), both code-index arrays and
+    both absmax arrays identical after every step; masked-out parameters keep zero moments; an all-zero block stays exactly zero."""
+    from multimodal_unlearning_b200 import norms, salun
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(n)
+    p = torch.randn(n, generator=g).to(torch.bfloat16)
+    mask = (torch.rand(n, generator=g) < 0.5).to(torch.int8).numpy() if mask_kind != "none" else None
+    c1, c2 = salun.dynamic_codebook(True).numpy(), salun.dynamic_codebook(False).numpy()
+    s1, s2, a1, a2 = salun.adamw8_init(n, dev)
+    o1, o2, oa1, oa2 = s1.cpu().numpy(), s2.cpu().numpy(), a1.cpu().numpy(), a2.cpu().numpy()
+    pd, po = p.to(dev), p.clone()
+    md = None
+    if mask is not None:
+        md = torch.from_numpy(mask).to(dev)
+        if mask_kind == "bits":
+            md = salun.pack_mask(md)
+    hyper = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)
+    for step in range(1, 5):
+        gr = (torch.randn(n, generator=g) * (0.0 if step == 3 else 10.0 ** torch.randint(-4, 1, (1,), generator=g).item())).to(torch.bfloat16)
+        gr[:512] = 0                                               # two blocks that never see a gradient
+        scale = None
+        if step == 4:                                              # fused clipping coefficient on the last step
+            sumsq = norms.grad_sqnorm([gr.to(dev)], [md])
+            scale = norms.clip_coef(sumsq, 0.5)
+        salun.masked_adamw8_flat(pd, gr.to(dev), s1, s2, a1, a2, md, step, lr=1e-3, grad_scale=scale)
+        po, o1, o2, oa1, oa2 = SO.adamw8_step(po, gr, o1, o2, oa1, oa2, mask, step, code1=c1, code2=c2,
+                                              grad_scale=float(scale.item()) if scale is not None else None, **hyper)
+        torch.cuda.synchronize()
+        assert torch.equal(pd.cpu().view(torch.int16), po.view(torch.int16)), step
+        assert np.array_equal(s1.cpu().numpy(), o1) and np.array_equal(s2.cpu().numpy(), o2), step
+        assert np.array_equal(a1.cpu().numpy(), oa1) and np.array_equal(a2.cpu().numpy(), oa2), step
+    assert a1[:2].abs().sum().item() == 0 and a2[:2].abs().sum().item() == 0
+    if mask is not None:
+        zero1, zero2 = int(np.nonzero(c1 == 0)[0][0]), int(np.nonzero(c2 == 0)[0][0])
+        off = mask == 0
+        assert np.all(s1.cpu().numpy()[off] == zero1) and np.all(s2.cpu().numpy()[off] == zero2)
+
+
+def test_adamw8_tracks_fp32_states_and_saves_memory():
+    """MaskedAdamW(state_bits=8) against the fp32-state optimiser over 30 steps on the same gradients: the parameters stay
+    within a small multiple of bf16 resolution of each other; optimiser state is 2 bytes + 8/256 per parameter instead of 8."""
+    from multimodal_unlearning_b200 import salun
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    shapes = [(512, 384), (4096,), (100,)]                          # the 100-element tensor keeps fp32 moments
+    base = [torch.randn(*s, generator=g).to(torch.bfloat16) for s in shapes]
+    p32 = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
+    p8 = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
+    o32 = salun.MaskedAdamW(p32, lr=1e-3, weight_decay=0.0)
+    o8 = salun.MaskedAdamW(p8, lr=1e-3, weight_decay=0.0, state_bits=8)
+    for _ in range(30):
+        for a, b in zip(p32, p8):
+            gr = (0.1 * torch.randn(a.shape, generator=g)).to(torch.bfloat16).to(dev)
+            a.grad, b.grad = gr, gr.clone()
+        o32.step()
+        o8.step()
+    for a, b, b0 in zip(p32, p8, base):
+        moved = (a.detach().float().cpu() - b0.float()).abs().mean().item()
+        diff = (a.detach().float() - b.detach().float()).abs().mean().item()
+        assert moved > 0 and diff <= 0.08 * moved, (diff, moved)    # the 8-bit trajectory follows the fp32 one
+    st = o8.state[p8[0]]
+    assert st["state1"].dtype == torch.uint8 and st["state1"].numel() == p8[0].numel() and "exp_avg" not in st
+    assert "exp_avg" in o8.state[p8[2]]
+    bytes8 = sum(t.numel() * t.element_size() for k, t in st.items() if torch.is_tensor(t))
+    assert bytes8 <= (2 + 8 / 256) * p8[0].numel() + 16

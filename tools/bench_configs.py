@@ -51,7 +51,7 @@ def timed(fn, steps=10, warmup=3):
     return a.elapsed_time(b) / steps
 
 
-def main():
+def run(steps=10, warmup=3, write=False):
     out = []
     w64 = (0.02 * torch.randn(32064, H, device=dev, generator=torch.Generator(device=dev).manual_seed(1))).to(torch.bfloat16)
     w00 = w64[:32000].contiguous()
@@ -102,6 +102,9 @@ def main():
     def cfg4_compact():
         head.head_loss_fwd_bwd(hid, w64, KIND_CE, labels=yi, reduction="seq_mean", n_seqs=8, compact_ignored=True)
 
+    def cfg5_compact_dense():
+        head.head_loss_fwd_bwd(hid, w00, KIND_CE, labels=y5, coef=-1.0, compact_ignored=True)
+
     nhv = lambda v: n * H * v
     cases = [("cfg2 npo (N=8192, V=32064, teacher projected)", cfg2, n, 8 * nhv(32064)),
              ("cfg3 grad_diff_forget_ce_retain_kl (2 x N=8192, V=32064, fp32 dW accumulation across splits)", cfg3, 2 * n, 14 * nhv(32064)),
@@ -110,13 +113,17 @@ def main():
              ("cfg5 grad_ascent nlp (N=8192, V=32000)", cfg5, n, 6 * nhv(32000)),
              ("cfg5, 65 % of the rows ignored (image + question), all rows evaluated like the reference", cfg5_real, n, 6 * nhv(32000)),
              ("cfg5, 65 % ignored, compact_ignored=True (flops counted for all rows: the reference's work)", cfg5_real_compact, n, 6 * nhv(32000)),
-             ("cfg4 dpo shipped semantics, compact_ignored=True (5-15 valid rows per sequence of 1024)", cfg4_compact, n, 6 * nhv(32064))]
+             ("cfg4 dpo shipped semantics, compact_ignored=True (5-15 valid rows per sequence of 1024)", cfg4_compact, n, 6 * nhv(32064)),
+             ("cfg5 dense labels, compact_ignored=True (every row valid: the cost of the row map itself)", cfg5_compact_dense, n, 6 * nhv(32000))]
     for name, fn, tokens, flops in cases:
-        ms = timed(fn)
+        ms = timed(fn, steps, warmup)
         tf = flops / ms / 1e9
         out.append({"config": name, "ms_per_step": ms, "tokens_per_s": tokens / ms * 1e3, "algorithmic_tflops": flops / 1e12,
                     "tflops_per_s": tf, "frac_sustained_peak": tf / P_SUS, "frac_burst_peak": tf / P_BURST})
-        print(json.dumps(out[-1]), flush=True)
+        if write:
+            print(json.dumps(out[-1]), flush=True)
+    if not write:
+        return out
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "configs_bench.json").write_text(json.dumps(out, indent=1))
     md = ["# Loss-head throughput on every BASELINE.json config (one B200, device-resident inputs)\n",
@@ -133,5 +140,8 @@ def main():
     (ROOT / "gpurun_out" / "configs_bench.md").write_text("\n".join(md) + "\n")
 
 
+    return out
+
+
 if __name__ == "__main__":
-    main()
+    run(write=True)

@@ -50,7 +50,14 @@ def run(layers=32, reps=3, peak_gbs=6525.2, adam=True):
     sel = st.select(ths)
     ms = timed(lambda: st.select(ths))
     out["histogram+select(10 thresholds)"] = {"ms": ms, "bytes_per_param": 2, "gbs": 2 * P / ms / 1e6, "frac": 2 * P / ms / 1e6 / peak_gbs}
+    ms = timed(lambda: st.select(ths, scope="global"))
+    out["histogram+select(10 thresholds, global scope)"] = {"ms": ms, "bytes_per_param": 2, "gbs": 2 * P / ms / 1e6,
+                                                            "frac": 2 * P / ms / 1e6 / peak_gbs}
     mask = torch.empty(P, dtype=torch.int8, device=dev)
+    sel_g = st.select(ths, scope="global")
+    ms = timed(lambda: st.mask_flat(sel_g, 4, out=mask))
+    out["mask(one threshold, global scope)"] = {"ms": ms, "bytes_per_param": 3, "gbs": 3 * P / ms / 1e6, "frac": 3 * P / ms / 1e6 / peak_gbs,
+                                               "ones": int(mask.sum(dtype=torch.int64).item()), "expected_ones": int(ths[4] * sum(lay.numels))}
     ms = timed(lambda: st.mask_flat(sel, 4, out=mask))
     out["mask(one threshold)"] = {"ms": ms, "bytes_per_param": 3, "gbs": 3 * P / ms / 1e6, "frac": 3 * P / ms / 1e6 / peak_gbs,
                                   "ones": int(mask.sum(dtype=torch.int64).item())}
