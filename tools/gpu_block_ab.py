@@ -20,14 +20,18 @@ sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "8192
 rounds, steps = 7, 8
 
 
+OVERLAP = len(sys.argv) > 2 and sys.argv[2] == "overlap"
+
+
 def run(kind, br):
+    ov = OVERLAP and br < N
     if kind == "npo":
-        head.head_loss_fwd_bwd(hid, w, KIND_NPO, ref_hidden=ref, ref_weight=w, beta=1.0, block_rows=br)
+        head.head_loss_fwd_bwd(hid, w, KIND_NPO, ref_hidden=ref, ref_weight=w, beta=1.0, block_rows=br, overlap=ov)
     else:
-        head.head_loss_fwd_bwd(hid, w, KIND_CE, labels=y, block_rows=br)
+        head.head_loss_fwd_bwd(hid, w, KIND_CE, labels=y, block_rows=br, overlap=ov)
 
 
-out = {}
+out = {"overlap": OVERLAP}
 for kind in ("npo", "ce"):
     times = {br: [] for br in sizes}
     for br in sizes:
@@ -47,4 +51,4 @@ for kind in ("npo", "ce"):
     out[kind] = {str(br): {"ms_median": med[br], "ms_min": min(times[br]), "vs_largest": med[br] / med[sizes[0]]} for br in sizes}
     print(kind, json.dumps(out[kind]), flush=True)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / "block_ab.json").write_text(json.dumps(out, indent=1))
+(ROOT / "gpurun_out" / ("block_ab_overlap.json" if OVERLAP else "block_ab.json")).write_text(json.dumps(out, indent=1))
