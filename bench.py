@@ -545,6 +545,13 @@ def main():
     drain()
     barrier()
     launches_per_step = res.launches * (2 if multi_split else 1) + (1 if fused else 0)   # + the all-gather kernel of the fused all-reduce
+    # peak device memory one step adds on top of its inputs and the weights (workspace with the staged logits + outputs)
+    torch.cuda.reset_peak_memory_stats()
+    mem0 = torch.cuda.memory_allocated()
+    step(0, dev_in)
+    drain()
+    torch.cuda.synchronize()
+    head_peak_extra = int(torch.cuda.max_memory_allocated() - mem0)
     nv0 = _nvlink_counters(local) if world > 1 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -688,7 +695,7 @@ def main():
             "config": {"workload": cfg["workload"], "baseline_config": cfg["baseline"], "loss_type": cfg["loss_type"], "rows_per_gpu": n * cfg["splits"],
                        "hidden": H, "vocab": V, "block_rows": block_rows or head.DEFAULT_BLOCK_ROWS, "row_compaction": bool(compact),
                        "ce_rows_with_a_label": ce_valid_rows if args.config != 2 else None,
-                       "loss": loss_value,
+                       "loss": loss_value, "peak_extra_bytes_per_step": head_peak_extra,
                        "l2": "inputs larger than L2 (W 263 MB + hidden 2 x 67 MB + staged logits vs 126 MB L2); no explicit flush",
                        "dw_allreduce": ("SKIPPED (--no-allreduce diagnostic run)" if args.no_allreduce else
                                         ("fused: dW contraction epilogue TMA-reduce-adds tiles into the owner rank's buffer over NVLink "

@@ -108,6 +108,10 @@ typedef struct ClearProjectArgs {
   int32_t n_rows_dev_offset;
 } ClearProjectArgs;
 int clear_head_project(const ClearProjectArgs* args, void* stream);
+/* The student's and the frozen teacher's projection of the same rows as ONE launch (two independent contractions whose
+ * work items share the persistent grid: one pipeline ramp and one tail instead of two).  Both must agree in lse_part
+ * presence, cta_group and n_rows_dev. */
+int clear_head_project_pair(const ClearProjectArgs* student, const ClearProjectArgs* teacher, void* stream);
 /* Same statistics for teacher logits handed over already materialised (`self.teacher_model(**x).logits`,
  * mm/trainer.py:199-200): lse_part float2 [n_rows][clear_head_vtiles(vocab)] from bf16 logits. */
 int clear_head_lse_partials(const void* logits, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,

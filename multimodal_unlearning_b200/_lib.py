@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     # ABI 3
     "clear_head_lse_partials_f32", "clear_rows_gather_dev", "clear_rows_scatter_dev", "clear_index_compose",
     "clear_saliency_hist_total", "clear_saliency_select_global_tau", "clear_saliency_select_global_fill",
-    "clear_adamw8_block_elems", "clear_masked_adamw_8bit",
+    "clear_adamw8_block_elems", "clear_masked_adamw_8bit", "clear_head_project_pair",
 )
 ABI_VERSION = 3
 
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
     lib.clear_gemm_bf16.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.clear_head_vtiles.argtypes = [C.c_int]
     lib.clear_head_project.argtypes = [C.POINTER(ProjectArgs), C.c_void_p]
+    lib.clear_head_project_pair.argtypes = [C.POINTER(ProjectArgs), C.POINTER(ProjectArgs), C.c_void_p]
     lib.clear_head_lse_partials.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.clear_head_rowloss.argtypes = [C.POINTER(RowLossArgs), C.c_void_p]
     lib.clear_head_count_valid.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

@@ -50,6 +50,24 @@ int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d
                      int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits = 1,
                      void* const* peer_d = nullptr, int n_peers = 0, GemmDyn dyn = GemmDyn());
 int current_device();   // ordinal of the current device, < 0 on error (per-device caches)
+// One contraction D[m, n] = A[m, k] B[n, k]^T of a launch (see GemmProblem in gemm_sm100.cuh).
+struct GemmDesc {
+  GemmOperand a, b;
+  void* d = nullptr;
+  int d_is_f32 = 0;
+  int64_t ldd = 0;
+  int m = 0, n = 0, k = 0;
+  float* lse_part = nullptr;
+  int reduce_add = 0;
+  int raster_m_fast = -1;       // < 0: the traffic model picks the tile order
+  void* const* peer_d = nullptr;
+  int n_peers = 0;
+  int dyn_dim = 0;              // 1: m, 2: k is bounded by the launch's device-side count
+};
+// One launch over one or two independent problems that share B's major and the epilogue kind: a single list of work items
+// (the first problem's first), one pipeline ramp and one tail instead of two.
+int launch_gemm_group(int cta_group, const GemmDesc& first, const GemmDesc* second, cudaStream_t stream, int k_splits = 1,
+                      const int* dyn_count = nullptr, int dyn_offset = 0, int dyn_splits = 0);
 // Rows [row0, row1) of an [m, *] output that rank `rank` of `n_peers` owns under that sharding.
 void gemm_peer_rows(int cta_group, int m, int n_peers, int rank, int* row0, int* row1);
 // Number of K splits (1..4) that best fills the last wave of CTA groups for this problem.

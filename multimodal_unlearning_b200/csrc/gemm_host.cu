@@ -126,8 +126,7 @@ static int next_work_counter(unsigned int** out) {
 }
 
 template <int kCtaGroup, int kMajorA, int kMajorB, int kEpi>
-static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const PeerMaps& peers,
-                          const GemmParams& p, cudaStream_t stream) {
+static int launch_variant(const CUtensorMap (&tm)[6], const PeerMaps& peers, const GemmParams& p, cudaStream_t stream) {
   using S = GemmShape<kCtaGroup>;
   auto kern = gemm_bf16_kernel<kCtaGroup, kMajorA, kMajorB, kEpi>;
   static std::atomic<bool> configured[kMaxDevices] = {};  // per template instantiation and device (the attribute is per device)
@@ -139,9 +138,10 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   const int sms = device_sm_count();
   if (sms <= 0) return fail(CLEAR_ERR_DEVICE, "cannot query SM count");
-  const int tiles = p.m_tiles * p.n_tiles * (p.dyn_splits ? 4 : p.k_splits);
+  long long tiles = (long long)p.q[0].m_tiles * p.q[0].n_tiles * (p.dyn_splits ? 4 : p.k_splits);
+  if (p.n_problems > 1) tiles += (long long)p.q[1].m_tiles * p.q[1].n_tiles;
   int groups = sms / kCtaGroup;
-  if (groups > tiles) groups = tiles;
+  if (groups > tiles) groups = (int)tiles;
   GemmParams pl = p;
   pl.sm_groups = groups;
   cudaLaunchConfig_t cfg = {};
@@ -156,7 +156,7 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CLEAR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, peers, pl));
+  CLEAR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], peers, pl));
   return 0;
 }
 
@@ -236,103 +236,148 @@ static bool raster_override(int* m_fast, int* group) {
   return ov.on;
 }
 
-int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
-                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits,
-                     void* const* peer_d, int n_peers, GemmDyn dyn) {
-  if (!a.ptr || !b.ptr || !d) return fail(CLEAR_ERR_NULL, "gemm: null operand");
+// One problem of a launch: argument checks, tensor maps, tile order.
+static int fill_problem(int cta_group, const GemmDesc& g, CUtensorMap* tmA, CUtensorMap* tmB, CUtensorMap* tmD, GemmProblem* q,
+                        PeerMaps* peer_maps, bool* uses_peers) {
+  const GemmOperand &a = g.a, &b = g.b;
+  const int m = g.m, n = g.n, k = g.k;
+  if (!a.ptr || !b.ptr || !g.d) return fail(CLEAR_ERR_NULL, "gemm: null operand");
   if (m <= 0 || n <= 0 || k <= 0) return fail(CLEAR_ERR_SHAPE, "gemm: non-positive dims m=%d n=%d k=%d", m, n, k);
-  if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
-  if (cta_group != 1 && cta_group != 2) return fail(CLEAR_ERR_KIND, "gemm: cta_group must be 0, 1 or 2");
-  if ((a.ld % 8) || (b.ld % 8) || (ldd % (d_is_f32 ? 4 : 8)))
+  if ((a.ld % 8) || (b.ld % 8) || (g.ldd % (g.d_is_f32 ? 4 : 8)))
     return fail(CLEAR_ERR_ALIGN, "gemm: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld ldd=%lld)",
-                (long long)a.ld, (long long)b.ld, (long long)ldd);
-  if ((reinterpret_cast<uintptr_t>(a.ptr) | reinterpret_cast<uintptr_t>(b.ptr) | reinterpret_cast<uintptr_t>(d)) & 15)
+                (long long)a.ld, (long long)b.ld, (long long)g.ldd);
+  if ((reinterpret_cast<uintptr_t>(a.ptr) | reinterpret_cast<uintptr_t>(b.ptr) | reinterpret_cast<uintptr_t>(g.d)) & 15)
     return fail(CLEAR_ERR_ALIGN, "gemm: pointers must be 16-byte aligned");
   if (a.major == kMajorMN && a.ld < m) return fail(CLEAR_ERR_SHAPE, "gemm: MN-major A needs lda >= m");
   if (b.major == kMajorMN && b.ld < n) return fail(CLEAR_ERR_SHAPE, "gemm: MN-major B needs ldb >= n");
   if (a.major == kMajorK && a.ld < k) return fail(CLEAR_ERR_SHAPE, "gemm: lda < k");
   if (b.major == kMajorK && b.ld < k) return fail(CLEAR_ERR_SHAPE, "gemm: ldb < k");
-  if (ldd < n) return fail(CLEAR_ERR_SHAPE, "gemm: ldd < n");
-  if (lse_part && d_is_f32) return fail(CLEAR_ERR_KIND, "gemm: lse_part requires a bf16 output");
-  if (reduce_add && lse_part) return fail(CLEAR_ERR_KIND, "gemm: accumulate cannot be combined with lse_part");
-  if (k_splits < 1) k_splits = 1;
-  if (k_splits > 1 && !reduce_add) return fail(CLEAR_ERR_KIND, "gemm: split-K requires the reduce-add epilogue (accumulate = 1)");
-
-  CUtensorMap tmA, tmB, tmD;
+  if (g.ldd < n) return fail(CLEAR_ERR_SHAPE, "gemm: ldd < n");
+  if (g.lse_part && g.d_is_f32) return fail(CLEAR_ERR_KIND, "gemm: lse_part requires a bf16 output");
+  if (g.reduce_add && g.lse_part) return fail(CLEAR_ERR_KIND, "gemm: accumulate cannot be combined with lse_part");
+  if (g.dyn_dim != 0 && g.dyn_dim != 1 && g.dyn_dim != 2) return fail(CLEAR_ERR_KIND, "gemm: dyn_dim must be 0, 1 (M) or 2 (K)");
   int rc;
-  if ((rc = make_operand_map(&tmA, a, m, k, 128))) return rc;
-  if ((rc = make_operand_map(&tmB, b, n, k, 256 / cta_group))) return rc;
-  if ((rc = make_output_map(&tmD, d, d_is_f32, ldd, m, n))) return rc;
+  if ((rc = make_operand_map(tmA, a, m, k, 128))) return rc;
+  if ((rc = make_operand_map(tmB, b, n, k, 256 / cta_group))) return rc;
+  if ((rc = make_output_map(tmD, g.d, g.d_is_f32, g.ldd, m, n))) return rc;
+  if (g.n_peers > 0) {
+    if (g.n_peers > kMaxPeers || !g.peer_d) return fail(CLEAR_ERR_SHAPE, "gemm: 1 <= n_peers <= %d with a pointer table required", kMaxPeers);
+    if (g.lse_part) return fail(CLEAR_ERR_KIND, "gemm: the peer-sharded epilogue excludes lse_part");
+    if (*uses_peers) return fail(CLEAR_ERR_KIND, "gemm: only one problem of a launch can be peer-sharded");
+    for (int r = 0; r < g.n_peers; ++r) {
+      if (!g.peer_d[r] || (reinterpret_cast<uintptr_t>(g.peer_d[r]) & 15)) return fail(CLEAR_ERR_ALIGN, "gemm: peer buffer %d is NULL or misaligned", r);
+      if ((rc = make_output_map(&peer_maps->tm[r], g.peer_d[r], g.d_is_f32, g.ldd, m, n))) return rc;
+    }
+    for (int r = g.n_peers; r < kMaxPeers; ++r) peer_maps->tm[r] = peer_maps->tm[0];
+    *uses_peers = true;
+  }
+  q->M = m; q->N = n; q->K = k;
+  q->m_tiles = (m + 128 * cta_group - 1) / (128 * cta_group);
+  q->n_tiles = (n + 255) / 256;
+  if (g.raster_m_fast < 0) {
+    pick_raster(cta_group, m, n, k, &q->raster_m_fast, &q->raster_group);
+  } else {
+    q->raster_m_fast = g.raster_m_fast ? 1 : 0;
+    q->raster_group = g.raster_m_fast ? q->m_tiles : q->n_tiles;  // whole-dimension chunks
+  }
+  raster_override(&q->raster_m_fast, &q->raster_group);
+  {
+    const int fast = q->raster_m_fast ? q->m_tiles : q->n_tiles;
+    if (q->raster_group > fast) q->raster_group = fast;
+    if (q->raster_group < 1) q->raster_group = 1;
+  }
+  q->reduce_add = g.reduce_add;
+  q->a_major = a.major;
+  q->lse_part = reinterpret_cast<float2*>(g.lse_part);
+  q->n_peers = g.n_peers;
+  q->mtiles_per_peer = g.n_peers > 0 ? peer_mtiles(cta_group, m, g.n_peers) : 1;
+  q->dyn_dim = g.dyn_dim;
+  return 0;
+}
+
+static int epilogue_kind(const GemmDesc& g) { return g.d_is_f32 ? kEpiStoreF32 : (g.lse_part ? kEpiStoreBF16Lse : kEpiStoreBF16); }
+
+// One launch over one or two problems (second == nullptr: one).  Two problems must agree in B's major and in the epilogue
+// kind; A's major may differ (the kernel is then instantiated with a run-time A major); no split-K.
+int launch_gemm_group(int cta_group, const GemmDesc& first, const GemmDesc* second, cudaStream_t stream, int k_splits,
+                      const int* dyn_count, int dyn_offset, int dyn_splits) {
+  if (cta_group == 0) cta_group = CLEAR_DEFAULT_CTA_GROUP;
+  if (cta_group != 1 && cta_group != 2) return fail(CLEAR_ERR_KIND, "gemm: cta_group must be 0, 1 or 2");
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > 1 && !first.reduce_add) return fail(CLEAR_ERR_KIND, "gemm: split-K requires the reduce-add epilogue (accumulate = 1)");
+  if (second && (k_splits > 1 || dyn_splits)) return fail(CLEAR_ERR_KIND, "gemm: a two-problem launch excludes split-K");
+  if (second && (second->b.major != first.b.major || epilogue_kind(*second) != epilogue_kind(first)))
+    return fail(CLEAR_ERR_KIND, "gemm: the two problems of a launch must share B's major and the epilogue kind");
+  if (first.n_peers > 0 && k_splits > 1) return fail(CLEAR_ERR_KIND, "gemm: the peer-sharded epilogue excludes split-K");
+
+  CUtensorMap tm[6];
   static PeerMaps no_peers = {};
   PeerMaps peer_maps_storage;
-  const PeerMaps* peers = &no_peers;
-  if (n_peers > 0) {
-    if (n_peers > kMaxPeers || !peer_d) return fail(CLEAR_ERR_SHAPE, "gemm: 1 <= n_peers <= %d with a pointer table required", kMaxPeers);
-    if (lse_part || k_splits > 1) return fail(CLEAR_ERR_KIND, "gemm: the peer-sharded epilogue excludes lse_part and split-K");
-    for (int r = 0; r < n_peers; ++r) {
-      if (!peer_d[r] || (reinterpret_cast<uintptr_t>(peer_d[r]) & 15)) return fail(CLEAR_ERR_ALIGN, "gemm: peer buffer %d is NULL or misaligned", r);
-      if ((rc = make_output_map(&peer_maps_storage.tm[r], peer_d[r], d_is_f32, ldd, m, n))) return rc;
-    }
-    for (int r = n_peers; r < kMaxPeers; ++r) peer_maps_storage.tm[r] = peer_maps_storage.tm[0];
-    peers = &peer_maps_storage;
-  }
-
-  GemmParams p;
-  p.M = m; p.N = n; p.K = k;
-  p.m_tiles = (m + 128 * cta_group - 1) / (128 * cta_group);
-  p.n_tiles = (n + 255) / 256;
-  if (raster_m_fast < 0) {
-    pick_raster(cta_group, m, n, k, &p.raster_m_fast, &p.raster_group);
+  bool uses_peers = false;
+  GemmParams p = {};
+  int rc;
+  if ((rc = fill_problem(cta_group, first, &tm[0], &tm[1], &tm[2], &p.q[0], &peer_maps_storage, &uses_peers))) return rc;
+  if (second) {
+    if ((rc = fill_problem(cta_group, *second, &tm[3], &tm[4], &tm[5], &p.q[1], &peer_maps_storage, &uses_peers))) return rc;
   } else {
-    p.raster_m_fast = raster_m_fast ? 1 : 0;
-    p.raster_group = raster_m_fast ? p.m_tiles : p.n_tiles;  // whole-dimension chunks
+    tm[3] = tm[0]; tm[4] = tm[1]; tm[5] = tm[2];
+    p.q[1] = p.q[0];
+    p.q[1].n_peers = 0;
   }
-  raster_override(&p.raster_m_fast, &p.raster_group);
+  p.n_problems = second ? 2 : 1;
   {
-    const int fast = p.raster_m_fast ? p.m_tiles : p.n_tiles;
-    if (p.raster_group > fast) p.raster_group = fast;
-    if (p.raster_group < 1) p.raster_group = 1;
-  }
-  p.reduce_add = reduce_add;
-  {
-    const int num_kb = (k + 63) / 64;
+    const int num_kb = (first.k + 63) / 64;
     if (k_splits > num_kb) k_splits = num_kb;
     p.k_splits = k_splits;
     p.kb_per_split = (num_kb + k_splits - 1) / k_splits;
     p.k_splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty item
   }
-  p.lse_part = reinterpret_cast<float2*>(lse_part);
   if ((rc = next_work_counter(&p.work_counter))) return rc;
-  p.n_peers = n_peers;
-  p.mtiles_per_peer = n_peers > 0 ? peer_mtiles(cta_group, m, n_peers) : 1;
-  p.dyn_count = dyn.count;
-  p.dyn_offset = dyn.offset;
-  p.dyn_dim = dyn.count ? dyn.dim : 0;
-  p.dyn_splits = (dyn.count && dyn.dim == 1) ? dyn.splits : 0;
+  const bool any_dyn = first.dyn_dim != 0 || (second && second->dyn_dim != 0);
+  p.dyn_count = any_dyn ? dyn_count : nullptr;
+  if (any_dyn && !dyn_count) return fail(CLEAR_ERR_NULL, "gemm: dyn_dim without a device-side count");
+  if (!p.dyn_count) { p.q[0].dyn_dim = 0; p.q[1].dyn_dim = 0; }
+  p.dyn_offset = dyn_offset;
+  p.dyn_splits = (p.dyn_count && first.dyn_dim == 1 && !second) ? dyn_splits : 0;
   p.sm_groups = 1;
-  if (p.dyn_dim != 0 && p.dyn_dim != 1 && p.dyn_dim != 2) return fail(CLEAR_ERR_KIND, "gemm: dyn.dim must be 1 (M) or 2 (K)");
-  if (p.dyn_dim == 2 && p.k_splits > 1) return fail(CLEAR_ERR_KIND, "gemm: a device-side K extent excludes split-K");
-  if (p.dyn_splits && !(reduce_add && d_is_f32)) return fail(CLEAR_ERR_KIND, "gemm: in-kernel split-K needs the fp32 reduce-add epilogue");
+  if (first.dyn_dim == 2 && p.k_splits > 1) return fail(CLEAR_ERR_KIND, "gemm: a device-side K extent excludes split-K");
+  if (p.dyn_splits && !(first.reduce_add && first.d_is_f32)) return fail(CLEAR_ERR_KIND, "gemm: in-kernel split-K needs the fp32 reduce-add epilogue");
 
-  const int epi = d_is_f32 ? kEpiStoreF32 : (lse_part ? kEpiStoreBF16Lse : kEpiStoreBF16);
+  const PeerMaps& peers = uses_peers ? peer_maps_storage : no_peers;
+  const int epi = epilogue_kind(first);
+  const int a_major = (second && second->a.major != first.a.major) ? (int)kMajorRuntime : first.a.major;
+  const int b_major = first.b.major;
 #define CLEAR_DISPATCH(CG, MA, MB, EPI)                                                     \
-  if (cta_group == CG && a.major == MA && b.major == MB && epi == EPI)                      \
-    return launch_variant<CG, MA, MB, EPI>(tmA, tmB, tmD, *peers, p, stream);
+  if (cta_group == CG && a_major == MA && b_major == MB && epi == EPI)                      \
+    return launch_variant<CG, MA, MB, EPI>(tm, peers, p, stream);
   CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16)
   CLEAR_DISPATCH(1, kMajorK, kMajorK, kEpiStoreBF16Lse)
   CLEAR_DISPATCH(1, kMajorK, kMajorMN, kEpiStoreBF16)
   CLEAR_DISPATCH(1, kMajorK, kMajorMN, kEpiStoreF32)
   CLEAR_DISPATCH(1, kMajorMN, kMajorMN, kEpiStoreBF16)
   CLEAR_DISPATCH(1, kMajorMN, kMajorMN, kEpiStoreF32)
+  CLEAR_DISPATCH(1, kMajorRuntime, kMajorMN, kEpiStoreBF16)
   CLEAR_DISPATCH(2, kMajorK, kMajorK, kEpiStoreBF16)
   CLEAR_DISPATCH(2, kMajorK, kMajorK, kEpiStoreBF16Lse)
   CLEAR_DISPATCH(2, kMajorK, kMajorMN, kEpiStoreBF16)
   CLEAR_DISPATCH(2, kMajorK, kMajorMN, kEpiStoreF32)
   CLEAR_DISPATCH(2, kMajorMN, kMajorMN, kEpiStoreBF16)
   CLEAR_DISPATCH(2, kMajorMN, kMajorMN, kEpiStoreF32)
+  CLEAR_DISPATCH(2, kMajorRuntime, kMajorMN, kEpiStoreBF16)
 #undef CLEAR_DISPATCH
   return fail(CLEAR_ERR_KIND, "gemm: operand layout combination (a_major=%d, b_major=%d, epilogue=%d) is not built",
-              a.major, b.major, epi);
+              a_major, b_major, epi);
+}
+
+int launch_gemm_bf16(int cta_group, GemmOperand a, GemmOperand b, void* d, int d_is_f32, int64_t ldd, int m, int n,
+                     int k, float* lse_part, int reduce_add, int raster_m_fast, cudaStream_t stream, int k_splits,
+                     void* const* peer_d, int n_peers, GemmDyn dyn) {
+  GemmDesc g;
+  g.a = a; g.b = b; g.d = d; g.d_is_f32 = d_is_f32; g.ldd = ldd; g.m = m; g.n = n; g.k = k;
+  g.lse_part = lse_part; g.reduce_add = reduce_add; g.raster_m_fast = raster_m_fast;
+  g.peer_d = peer_d; g.n_peers = n_peers;
+  g.dyn_dim = dyn.count ? dyn.dim : 0;
+  return launch_gemm_group(cta_group, g, nullptr, stream, k_splits, dyn.count, dyn.offset, dyn.splits);
 }
 
 }  // namespace clear

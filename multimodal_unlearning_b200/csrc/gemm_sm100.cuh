@@ -25,35 +25,45 @@
 
 namespace clear {
 
-enum OperandMajor : int { kMajorK = 0, kMajorMN = 1 };
+enum OperandMajor : int { kMajorK = 0, kMajorMN = 1, kMajorRuntime = 2 /* A only: GemmProblem::a_major */ };
 enum EpilogueKind : int {
   kEpiStoreBF16 = 0,     // D bf16
   kEpiStoreBF16Lse = 1,  // D bf16 + per-(row, n-tile) (max, sum-exp) partials
   kEpiStoreF32 = 2,      // D fp32 (store or reduce-add)
 };
 
-struct GemmParams {
+// One contraction of a launch.  A launch runs one problem, or TWO independent problems that share the operand majors of B
+// and the epilogue kind (student + teacher projection; dH + dW of one block of rows): their work items form one list, the
+// first problem's (longer) tiles first, so that the CTA pairs that finish the first problem early start on the second
+// instead of idling until a kernel boundary — one pipeline ramp and one tail per pair of contractions instead of two.
+struct GemmProblem {
   int M, N, K;
   int m_tiles, n_tiles;  // in units of (128*cta_group) x 256
   int raster_m_fast;     // 1: consecutive tiles walk M first (A small / re-read from L2), 0: N first
   int raster_group;      // tiles of the fast dimension per chunk: a chunk is swept across the whole slow dimension before
                          // the next chunk starts, so that the chunk's operand stays in L2 (see pick_raster in gemm_host.cu)
   int reduce_add;        // accumulate into D instead of overwriting (TMA reduce-add; bf16 D rounds after each add)
-  int k_splits;          // > 1: each output tile is cut into k_splits work items along K (fp32 reduce-add epilogue)
-  int kb_per_split;      // K blocks (of 64) per work item
+  int a_major;           // operand A's major when the kernel is instantiated with kMajorRuntime
   float2* lse_part;      // [M][n_tiles] when kEpiStoreBF16Lse
+  int n_peers;           // > 0: the output is sharded by M tiles over the peers' buffers (fused reduce-scatter)
+  int mtiles_per_peer;   // owner of M tile mt = min(n_peers - 1, mt / mtiles_per_peer)
+  int dyn_dim;           // 0: extents as given; 1: M, 2: K comes from *dyn_count (see GemmParams)
+};
+
+struct GemmParams {
+  GemmProblem q[2];
+  int n_problems;
+  int k_splits;          // > 1 (single problem only): each output tile is cut into k_splits work items along K (fp32 reduce-add epilogue)
+  int kb_per_split;      // K blocks (of 64) per work item
   unsigned int* work_counter;  // [0] next unclaimed work item (dynamic tile scheduler), [1] CTA groups that have finished;
                                // both zero at launch: the last group to finish resets them, so no memset node sits between
                                // two launches on a stream
-  int n_peers;                 // > 0: the output is sharded by M tiles over the peers' buffers (fused reduce-scatter)
-  int mtiles_per_peer;         // owner of M tile mt = min(n_peers - 1, mt / mtiles_per_peer)
   // Device-side extent (row compaction without a host round trip): *dyn_count - dyn_offset, clamped to [0, M or K], replaces
   // M (dyn_dim = 1: projection / dH over the valid rows only) or K rounded up to a K block (dyn_dim = 2: dW; the operand
   // rows of the last block beyond the count must be zero).  The tensor maps, the grid and the tile order are those of the
-  // host-side maximum.  dyn_dim = 1 with dyn_splits: the number of K splits is chosen in the kernel from the actual M.
+  // host-side maximum.  dyn_splits (single problem, dyn_dim = 1): the number of K splits is chosen in the kernel from the actual M.
   const int* dyn_count;
   int dyn_offset;
-  int dyn_dim;
   int dyn_splits;              // 1: choose k_splits in-kernel (fp32 reduce-add epilogue, D pre-zeroed); 0: k_splits as given
   int sm_groups;               // CTA groups of the launch (in-kernel split choice)
 };
@@ -114,7 +124,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_major, int
 template <int kCtaGroup, int kMajorA, int kMajorB, int kEpi>
 __global__ void __launch_bounds__(GemmShape<kCtaGroup>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ PeerMaps peers, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmD1,
+                 const __grid_constant__ PeerMaps peers, const GemmParams p) {
   using S = GemmShape<kCtaGroup>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_addr = ptx::smem_u32(smem_raw);
@@ -137,12 +149,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t cta_rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool two = p.n_problems > 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     ptx::prefetch_tensormap(&tmD);
-    for (int r = 0; r < p.n_peers; ++r) ptx::prefetch_tensormap(&peers.tm[r]);
+    if (two) {
+      ptx::prefetch_tensormap(&tmA1);
+      ptx::prefetch_tensormap(&tmB1);
+      ptx::prefetch_tensormap(&tmD1);
+    }
+    const int np = max(p.q[0].n_peers, p.q[1].n_peers);
+    for (int r = 0; r < np; ++r) ptx::prefetch_tensormap(&peers.tm[r]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
@@ -168,49 +187,77 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  // Device-side extents (see GemmParams::dyn_count): every thread derives the same values.
-  int dynM = p.M, dynK = p.K, m_tiles = p.m_tiles, k_splits = p.k_splits, kb_per_split = p.kb_per_split;
-  if (p.dyn_dim != 0) {
-    int c = *p.dyn_count - p.dyn_offset;
-    c = max(c, 0);
-    if (p.dyn_dim == 1) {
-      dynM = min(c, p.M);
-      m_tiles = (dynM + S::BM * kCtaGroup - 1) / (S::BM * kCtaGroup);
-      if (p.dyn_splits) {  // same rule as gemm_pick_k_splits (gemm_host.cu), on the actual number of output tiles
-        const int tiles = m_tiles * p.n_tiles, num_kb = (p.K + S::BK - 1) / S::BK;
-        int best = 1;
-        float best_eff = 0.f;
-        for (int sp = 1; sp <= 4 && tiles > 0; ++sp) {
-          if (sp > 1 && num_kb / sp < 64) break;
-          const float waves = (float)tiles * sp / (float)p.sm_groups;
-          const float eff = waves / ceilf(waves - 1e-6f);
-          if (eff > best_eff + 0.03f) { best_eff = eff; best = sp; }
-        }
-        kb_per_split = (num_kb + best - 1) / best;
-        k_splits = (num_kb + kb_per_split - 1) / kb_per_split;
+  // Extents of the (up to two) problems; device-side ones (see GemmParams::dyn_count) are resolved here: every thread
+  // derives the same values.
+  int M0 = p.q[0].M, K0 = p.q[0].K, mt0 = p.q[0].m_tiles;
+  int M1 = p.q[1].M, K1 = p.q[1].K, mt1 = p.q[1].m_tiles;
+  int k_splits = p.k_splits, kb_per_split = p.kb_per_split;
+  if (p.dyn_count != nullptr) {
+    const int c = max(*p.dyn_count - p.dyn_offset, 0);
+    auto resolve = [&](const GemmProblem& q, int& M, int& K, int& mt) {
+      if (q.dyn_dim == 1) {
+        M = min(c, q.M);
+        mt = (M + S::BM * kCtaGroup - 1) / (S::BM * kCtaGroup);
+      } else if (q.dyn_dim == 2) {
+        K = min((c + S::BK - 1) / S::BK * S::BK, (q.K + S::BK - 1) / S::BK * S::BK);
       }
-    } else {
-      dynK = min((c + S::BK - 1) / S::BK * S::BK, (p.K + S::BK - 1) / S::BK * S::BK);
-      kb_per_split = (dynK + S::BK - 1) / S::BK;  // dyn_dim = 2 excludes split-K
+    };
+    resolve(p.q[0], M0, K0, mt0);
+    if (two) resolve(p.q[1], M1, K1, mt1);
+    if (p.dyn_splits && p.q[0].dyn_dim == 1) {  // same rule as gemm_pick_k_splits (gemm_host.cu), on the actual number of output tiles
+      const int tiles = mt0 * p.q[0].n_tiles, num_kb = (p.q[0].K + S::BK - 1) / S::BK;
+      int best = 1;
+      float best_eff = 0.f;
+      for (int sp = 1; sp <= 4 && tiles > 0; ++sp) {
+        if (sp > 1 && num_kb / sp < 64) break;
+        const float waves = (float)tiles * sp / (float)p.sm_groups;
+        const float eff = waves / ceilf(waves - 1e-6f);
+        if (eff > best_eff + 0.03f) { best_eff = eff; best = sp; }
+      }
+      kb_per_split = (num_kb + best - 1) / best;
+      k_splits = (num_kb + kb_per_split - 1) / kb_per_split;
+    } else if (p.q[0].dyn_dim == 2) {
+      kb_per_split = (K0 + S::BK - 1) / S::BK;  // a device-side K excludes split-K
       k_splits = 1;
     }
   }
-  // Work item w = (output tile, K split): consecutive items are the splits of one tile.
-  const int num_tiles = m_tiles * p.n_tiles * k_splits;
-  const int num_kb_total = (dynK + S::BK - 1) / S::BK;   // 0 (no valid row at all): the epilogue emits zeros
+  // Work item w: problem 0's (output tile, K split) pairs — consecutive items are the splits of one tile — then problem 1's tiles.
+  const int base1 = mt0 * p.q[0].n_tiles * k_splits;
+  const int num_tiles = base1 + (two ? mt1 * p.q[1].n_tiles : 0);
+  const int nkb0 = (K0 + S::BK - 1) / S::BK;   // 0 (no valid row at all): the epilogue emits zeros
+  const int nkb1 = (K1 + S::BK - 1) / S::BK;
 
-  // Work item -> output tile.  Chunks of `raster_group` tiles along the fast dimension, each swept across the slow one.
-  auto tile_coords = [&](int t, int& mt, int& nt) {
-    const int fast_tiles = p.raster_m_fast ? m_tiles : p.n_tiles;
-    const int slow_tiles = p.raster_m_fast ? p.n_tiles : m_tiles;
-    const int per_chunk = p.raster_group * slow_tiles;
+  // Work item -> problem, output tile, K-block range.  Chunks of `raster_group` tiles along the fast dimension, each swept
+  // across the slow one.
+  struct Item {
+    int second, mt, nt, kb0, kb1;
+  };
+  auto decode = [&](int w) {
+    Item it;
+    it.second = (two && w >= base1) ? 1 : 0;
+    const GemmProblem& q = p.q[it.second];
+    const int m_tiles = it.second ? mt1 : mt0;
+    int t;
+    if (it.second) {
+      t = w - base1;
+      it.kb0 = 0;
+      it.kb1 = nkb1;
+    } else {
+      t = w / k_splits;
+      it.kb0 = (w % k_splits) * kb_per_split;
+      it.kb1 = min(nkb0, it.kb0 + kb_per_split);
+    }
+    const int fast_tiles = q.raster_m_fast ? m_tiles : q.n_tiles;
+    const int slow_tiles = q.raster_m_fast ? q.n_tiles : m_tiles;
+    const int per_chunk = q.raster_group * slow_tiles;
     const int c = t / per_chunk;
     const int r = t - c * per_chunk;
-    const int g = min(p.raster_group, fast_tiles - c * p.raster_group);
+    const int g = min(q.raster_group, fast_tiles - c * q.raster_group);
     const int slow = r / g;
-    const int fast = c * p.raster_group + (r - slow * g);
-    mt = p.raster_m_fast ? fast : slow;
-    nt = p.raster_m_fast ? slow : fast;
+    const int fast = c * q.raster_group + (r - slow * g);
+    it.mt = q.raster_m_fast ? fast : slow;
+    it.nt = q.raster_m_fast ? slow : fast;
+    return it;
   };
 
   // Reader side of the scheduler ring.  Every reader consumes every slot in order, the end-of-work item (>= num_tiles)
@@ -255,14 +302,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       while (w < num_tiles) {
         unsigned int next_claim = 0;
         if (leader) next_claim = atomicAdd(p.work_counter, 1u);
-        const int t = w / k_splits;
-        const int kb0 = (w % k_splits) * kb_per_split;
-        const int kb1 = min(num_kb_total, kb0 + kb_per_split);
-        int mt, nt;
-        tile_coords(t, mt, nt);
-        const int m0 = (mt * kCtaGroup + (int)cta_rank) * S::BM;
-        const int n0 = nt * S::BN + (int)cta_rank * S::B_ROWS;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const Item it = decode(w);
+        const CUtensorMap* mA = it.second ? &tmA1 : &tmA;
+        const CUtensorMap* mB = it.second ? &tmB1 : &tmB;
+        const bool a_mn = (kMajorA == kMajorRuntime) ? (p.q[it.second].a_major == kMajorMN) : (kMajorA == kMajorMN);
+        const int m0 = (it.mt * kCtaGroup + (int)cta_rank) * S::BM;
+        const int n0 = it.nt * S::BN + (int)cta_rank * S::B_ROWS;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           ptx::mbar_wait(empty_bar + stage * 8, phase ^ 1u);
           const uint32_t fb = full_bar + stage * 8;
           if (cta_rank == 0) ptx::mbar_arrive_expect_tx(fb, S::STAGE_BYTES * kCtaGroup);
@@ -271,19 +317,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int k0 = kb * S::BK;
           // K-major: one box [rows][64 k].  MN-major: one box [64 k][64 mn] per 64-element MN chunk,
           // chunks 8 KB apart (= the descriptor's LBO).
-          if constexpr (kMajorA == kMajorK) {
-            ptx::tma_load_2d<kCtaGroup>(a_dst, &tmA, fb, k0, m0);
+          if (!a_mn) {
+            ptx::tma_load_2d<kCtaGroup>(a_dst, mA, fb, k0, m0);
           } else {
 #pragma unroll
             for (int c = 0; c < S::BM / 64; ++c)
-              ptx::tma_load_2d<kCtaGroup>(a_dst + c * (S::BK * 128), &tmA, fb, m0 + c * 64, k0);
+              ptx::tma_load_2d<kCtaGroup>(a_dst + c * (S::BK * 128), mA, fb, m0 + c * 64, k0);
           }
           if constexpr (kMajorB == kMajorK) {
-            ptx::tma_load_2d<kCtaGroup>(b_dst, &tmB, fb, k0, n0);
+            ptx::tma_load_2d<kCtaGroup>(b_dst, mB, fb, k0, n0);
           } else {
 #pragma unroll
             for (int c = 0; c < S::B_ROWS / 64; ++c)
-              ptx::tma_load_2d<kCtaGroup>(b_dst + c * (S::BK * 128), &tmB, fb, n0 + c * 64, k0);
+              ptx::tma_load_2d<kCtaGroup>(b_dst + c * (S::BK * 128), mB, fb, n0 + c * 64, k0);
           }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -298,20 +344,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================================== MMA issuer ============================================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc(S::BM * kCtaGroup, S::BN, kMajorA, kMajorB);
       // K-major: +32 B per UMMA_K inside the swizzle span; MN-major: +16 k-rows * 128 B.
-      constexpr uint32_t a_adv = (kMajorA == kMajorK) ? (S::UMMA_K * 2) : (S::UMMA_K * 128);
       constexpr uint32_t b_adv = (kMajorB == kMajorK) ? (S::UMMA_K * 2) : (S::UMMA_K * 128);
-      constexpr uint32_t a_lbo = (kMajorA == kMajorK) ? 16u : (S::BK * 128);
       constexpr uint32_t b_lbo = (kMajorB == kMajorK) ? 16u : (S::BK * 128);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
       for (int w = sched_read(slot, sphase); w < num_tiles; w = sched_read(slot, sphase)) {
-        const int kb0 = (w % k_splits) * kb_per_split;
-        const int kb1 = min(num_kb_total, kb0 + kb_per_split);
+        const Item it = decode(w);
+        const bool a_mn = (kMajorA == kMajorRuntime) ? (p.q[it.second].a_major == kMajorMN) : (kMajorA == kMajorMN);
+        const uint32_t idesc = make_idesc(S::BM * kCtaGroup, S::BN, a_mn ? 1 : 0, kMajorB);
+        const uint32_t a_adv = a_mn ? (S::UMMA_K * 128) : (S::UMMA_K * 2);
+        const uint32_t a_lbo = a_mn ? (uint32_t)(S::BK * 128) : 16u;
         ptx::mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * S::BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           ptx::mbar_wait(full_bar + stage * 8, phase);
           ptx::tcgen05_fence_after();
           const uint32_t a_src = smem_base + stage * S::STAGE_BYTES;
@@ -321,7 +367,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < S::BK / S::UMMA_K; ++k) {
             ptx::umma_f16<kCtaGroup>(d_tmem, adesc + ((k * a_adv) >> 4), bdesc + ((k * b_adv) >> 4), idesc,
-                                     ((kb - kb0) | k) != 0 ? 1u : 0u);
+                                     ((kb - it.kb0) | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit<kCtaGroup>(empty_bar + stage * 8);  // frees the smem slot once the MMAs retire
           if (++stage == S::STAGES) { stage = 0; phase ^= 1u; }
@@ -333,8 +379,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==============================================
-    const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may read
-    const uint32_t stg = epi_addr + q * S::EPI_WARP_BYTES;
+    const uint32_t q4 = warp & 3u;  // TMEM lane quadrant this warp may read
+    const uint32_t stg = epi_addr + q4 * S::EPI_WARP_BYTES;
     const uint32_t sw = (lane & 7u);
     uint32_t nstores = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
     while (true) {
@@ -342,18 +388,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) w = sched_read(slot, sphase);
       w = __shfl_sync(0xffffffffu, w, 0);
       if (w >= num_tiles) break;
-      const int t = w / k_splits;
-      int mt, nt;
-      tile_coords(t, mt, nt);
-      const int row0 = (mt * kCtaGroup + (int)cta_rank) * S::BM + (int)q * 32;
+      const Item it = decode(w);
+      const GemmProblem& q = p.q[it.second];
+      const int dynM = it.second ? M1 : M0;
+      const bool no_k = it.kb1 <= it.kb0;   // no MMA ran: the accumulator is not defined, the tile is all zeros
+      const int mt = it.mt, nt = it.nt;
+      const int row0 = (mt * kCtaGroup + (int)cta_rank) * S::BM + (int)q4 * 32;
       const int col0 = nt * S::BN;
       // destination: this rank's D, or the buffer of the rank that owns these rows (always reduce-add there)
-      const CUtensorMap* tmOut = &tmD;
-      if (p.n_peers > 0) tmOut = &peers.tm[min(p.n_peers - 1, mt / p.mtiles_per_peer)];
-      const bool reduce_out = p.reduce_add || p.n_peers > 0;
+      const CUtensorMap* tmOut = it.second ? &tmD1 : &tmD;
+      if (q.n_peers > 0) tmOut = &peers.tm[min(q.n_peers - 1, mt / q.mtiles_per_peer)];
+      const bool reduce_out = q.reduce_add || q.n_peers > 0;
       ptx::mbar_wait(tfull_bar + acc * 8, acc_phase);
       ptx::tcgen05_fence_after();
-      const uint32_t t_base = tmem_base + ((q * 32u) << 16) + acc * S::BN;
+      const uint32_t t_base = tmem_base + ((q4 * 32u) << 16) + acc * S::BN;
 
       if constexpr (kEpi == kEpiStoreF32) {
 #pragma unroll 1
@@ -364,7 +412,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
           ptx::tmem_ld_wait();
-          if (num_kb_total == 0) {  // no MMA ran: the accumulator is not defined
+          if (no_k) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
@@ -374,7 +422,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::st_shared_v4(rowp + (((uint32_t)j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < dynM && col0 + c * 32 < p.N) {
+          if (lane == 0 && row0 < dynM && col0 + c * 32 < q.N) {
             if (reduce_out) ptx::tma_reduce_add_2d(tmOut, buf, col0 + c * 32, row0);
             else            ptx::tma_store_2d(tmOut, buf, col0 + c * 32, row0);
           }
@@ -393,7 +441,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) ptx::tma_store_wait_read<1>();
           __syncwarp();
           ptx::tmem_ld_wait();
-          if (num_kb_total == 0) {  // no MMA ran: the accumulator is not defined
+          if (no_k) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v0[j] = 0u; v1[j] = 0u; }
           }
@@ -414,8 +462,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]));
-              x[2 * j] = (cbase + 2 * j < p.N) ? f.x : -INFINITY;
-              x[2 * j + 1] = (cbase + 2 * j + 1 < p.N) ? f.y : -INFINITY;
+              x[2 * j] = (cbase + 2 * j < q.N) ? f.x : -INFINITY;
+              x[2 * j + 1] = (cbase + 2 * j + 1 < q.N) ? f.y : -INFINITY;
               cmax = fmaxf(cmax, fmaxf(x[2 * j], x[2 * j + 1]));
             }
             const float new_max = fmaxf(run_max, cmax);
@@ -432,7 +480,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::st_shared_v4(rowp + (((uint32_t)j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < dynM && col0 + c * 64 < p.N) {
+          if (lane == 0 && row0 < dynM && col0 + c * 64 < q.N) {
             if (reduce_out) ptx::tma_reduce_add_2d(tmOut, buf, col0 + c * 64, row0);  // bf16 += (rounded in L2)
             else            ptx::tma_store_2d(tmOut, buf, col0 + c * 64, row0);
           }
@@ -441,7 +489,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if constexpr (kEpi == kEpiStoreBF16Lse) {
           const int row = row0 + (int)lane;
-          if (row < dynM) p.lse_part[(size_t)row * p.n_tiles + nt] = make_float2(run_max, run_sum);
+          if (row < dynM) q.lse_part[(size_t)row * q.n_tiles + nt] = make_float2(run_max, run_sum);
         }
       }
       // every tcgen05.ld of this accumulator stage has completed (wait::ld above): hand it back

@@ -810,7 +810,13 @@ extern "C" {
 
 int clear_head_vtiles(int vocab) { return (vocab + 255) / 256; }
 
-int clear_head_project(const ClearProjectArgs* a, void* stream) {
+// diagnostic switch CLEAR_GEMM_GROUP=0: every contraction is its own launch (the round-1 schedule); read once
+static bool group_launches() {
+  static const bool on = [] { const char* e = getenv("CLEAR_GEMM_GROUP"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
+static int project_desc(const ClearProjectArgs* a, GemmDesc* g) {
   if (!a) return fail(CLEAR_ERR_NULL, "clear_head_project: args is NULL");
   if (!a->hidden || !a->weight || !a->logits) return fail(CLEAR_ERR_NULL, "clear_head_project: null tensor");
   if (a->n_rows <= 0 || a->n_rows > INT32_MAX || a->hidden_dim <= 0 || a->vocab <= 0)
@@ -819,14 +825,36 @@ int clear_head_project(const ClearProjectArgs* a, void* stream) {
   if (a->logits_ld % 64 || a->logits_ld < a->vocab)
     return fail(CLEAR_ERR_SHAPE, "clear_head_project: logits_ld (%lld) must be a multiple of 64 and >= vocab",
                 (long long)a->logits_ld);
-  GemmOperand A{a->hidden, a->hidden_ld, kMajorK};
-  GemmOperand B{a->weight, a->weight_ld, kMajorK};
-  GemmDyn dyn;
-  dyn.count = a->n_rows_dev;
-  dyn.offset = a->n_rows_dev_offset;
-  dyn.dim = 1;
-  return launch_gemm_bf16(a->cta_group, A, B, a->logits, 0, a->logits_ld, (int)a->n_rows, a->vocab, a->hidden_dim,
-                          a->lse_part, 0, /*raster: traffic model*/ -1, static_cast<cudaStream_t>(stream), 1, nullptr, 0, dyn);
+  g->a = GemmOperand{a->hidden, a->hidden_ld, kMajorK};
+  g->b = GemmOperand{a->weight, a->weight_ld, kMajorK};
+  g->d = a->logits;
+  g->d_is_f32 = 0;
+  g->ldd = a->logits_ld;
+  g->m = (int)a->n_rows; g->n = a->vocab; g->k = a->hidden_dim;
+  g->lse_part = a->lse_part;
+  g->dyn_dim = a->n_rows_dev ? 1 : 0;
+  return 0;
+}
+
+int clear_head_project(const ClearProjectArgs* a, void* stream) {
+  GemmDesc g;
+  if (int rc = project_desc(a, &g)) return rc;
+  return launch_gemm_group(a->cta_group, g, nullptr, static_cast<cudaStream_t>(stream), 1, a->n_rows_dev, a->n_rows_dev_offset, 0);
+}
+
+int clear_head_project_pair(const ClearProjectArgs* student, const ClearProjectArgs* teacher, void* stream) {
+  GemmDesc g0, g1;
+  int rc;
+  if ((rc = project_desc(student, &g0)) || (rc = project_desc(teacher, &g1))) return rc;
+  if (!group_launches()) {
+    if ((rc = clear_head_project(student, stream))) return rc;
+    return clear_head_project(teacher, stream);
+  }
+  if ((student->lse_part == nullptr) != (teacher->lse_part == nullptr) || student->cta_group != teacher->cta_group ||
+      student->n_rows_dev != teacher->n_rows_dev || student->n_rows_dev_offset != teacher->n_rows_dev_offset)
+    return fail(CLEAR_ERR_KIND, "clear_head_project_pair: both projections must agree in lse_part presence, cta_group and the device-side row count");
+  return launch_gemm_group(student->cta_group, g0, &g1, static_cast<cudaStream_t>(stream), 1, student->n_rows_dev,
+                           student->n_rows_dev_offset, 0);
 }
 
 static int lse_partials_impl(const void* logits, bool f32, int64_t logits_ld, int64_t n_rows, int32_t vocab, float* lse_part,
@@ -1037,6 +1065,34 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
     return fail(CLEAR_ERR_SHAPE, "clear_head_backward: bad sizes");
   if (a->hidden_dim % 8) return fail(CLEAR_ERR_SHAPE, "clear_head_backward: hidden_dim must be a multiple of 8");
   int rc;
+  if (a->n_peers < 0 || a->n_peers > 8) return fail(CLEAR_ERR_SHAPE, "clear_head_backward: 0 <= n_peers <= 8");
+  if (a->n_peers > 0 && a->dweight_f32) return fail(CLEAR_ERR_KIND, "clear_head_backward: the peer reduce-scatter accumulates in bf16");
+  const bool want_dw = a->dweight || a->n_peers > 0;
+  // Both gradients, both bf16: ONE launch when dH on its own would leave its last wave of SM pairs mostly idle (few row
+  // tiles: small staging blocks, compacted rows) — the 501-K-block tiles of dH = dZ W come first, the shorter tiles of
+  // dW = dZ^T H fill the SMs that finish early, so dH needs no split-K scratch (no zeroing, no conversion pass) and the two
+  // share one pipeline ramp and one tail.  With full waves (8192 rows: 6.92 of 7) two launches measured 1.5 % faster
+  // (tools/r02_group_ab.sh, same box, alternating processes), so that case keeps them.
+  const bool dh_starved = a->n_rows_dev != nullptr ||
+                          gemm_pick_k_splits(a->cta_group, (int)a->n_rows, a->hidden_dim, a->vocab) > 1;
+  if (a->dhidden && want_dw && !a->dweight_f32 && dh_starved && group_launches()) {
+    if (!a->weight || !a->hidden) return fail(CLEAR_ERR_NULL, "clear_head_backward: weight and hidden are required");
+    GemmDesc gh, gw;
+    gh.a = GemmOperand{a->dlogits, a->dlogits_ld, kMajorK};
+    gh.b = GemmOperand{a->weight, a->weight_ld, kMajorMN};
+    gh.d = a->dhidden; gh.ldd = a->dhidden_ld;
+    gh.m = (int)a->n_rows; gh.n = a->hidden_dim; gh.k = a->vocab;
+    gh.dyn_dim = a->n_rows_dev ? 1 : 0;
+    gw.a = GemmOperand{a->dlogits, a->dlogits_ld, kMajorMN};
+    gw.b = GemmOperand{a->hidden, a->hidden_ld, kMajorMN};
+    gw.d = a->dweight ? a->dweight : a->dweight_peers[0]; gw.ldd = a->dweight_ld;
+    gw.m = a->vocab; gw.n = a->hidden_dim; gw.k = (int)a->n_rows;
+    gw.reduce_add = a->accumulate;
+    gw.peer_d = a->n_peers > 0 ? a->dweight_peers : nullptr;
+    gw.n_peers = a->n_peers;
+    gw.dyn_dim = a->n_rows_dev ? 2 : 0;
+    return launch_gemm_group(a->cta_group, gh, &gw, stream, 1, a->n_rows_dev, a->n_rows_dev_offset, 0);
+  }
   if (a->dhidden) {
     if (!a->weight) return fail(CLEAR_ERR_NULL, "clear_head_backward: dhidden requested but weight is NULL");
     // dH[n, h] = sum_v dZ[n, v] W[v, h]: A = dZ (K-major, K = vocab), B = W read MN-major.
@@ -1082,8 +1138,6 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
   }
   if (a->dweight || a->n_peers > 0) {
     if (!a->hidden) return fail(CLEAR_ERR_NULL, "clear_head_backward: dweight requested but hidden is NULL");
-    if (a->n_peers < 0 || a->n_peers > 8) return fail(CLEAR_ERR_SHAPE, "clear_head_backward: 0 <= n_peers <= 8");
-    if (a->n_peers > 0 && a->dweight_f32) return fail(CLEAR_ERR_KIND, "clear_head_backward: the peer reduce-scatter accumulates in bf16");
     // dW[v, h] = sum_n dZ[n, v] H[n, h]: both operands read MN-major (K = rows).
     GemmOperand A{a->dlogits, a->dlogits_ld, kMajorMN};
     GemmOperand B{a->hidden, a->hidden_ld, kMajorMN};

@@ -212,22 +212,24 @@ int clear_head_loss_fwd_bwd(const ClearHeadArgs* a, void* workspace, size_t ws_b
     pa.hidden_ld = hidden_ld; pa.weight_ld = a->weight_ld; pa.logits_ld = p.ld;
     pa.n_rows = rows; pa.hidden_dim = a->hidden_dim; pa.vocab = a->vocab; pa.cta_group = a->cta_group;
     pa.n_rows_dev = count_dev; pa.n_rows_dev_offset = (int32_t)r0;
-    if ((rc = clear_head_project(&pa, stream))) return rc;
 
     const void* ref_rows = nullptr;
     int64_t ref_ld = 0;
     int ref_f32 = 0;
-    if (p.project_teacher) {
+    if (p.project_teacher) {   // student and teacher projections: two independent contractions, one launch
       ClearProjectArgs ta = pa;
       ta.hidden = static_cast<const uint8_t*>(ref_hidden) + r0 * ref_hidden_ld * esz;
       ta.weight = a->ref_weight;
       ta.logits = zr;
       ta.lse_part = rpart;
       ta.hidden_ld = ref_hidden_ld; ta.weight_ld = a->ref_weight_ld;
-      if ((rc = clear_head_project(&ta, stream))) return rc;
+      if ((rc = clear_head_project_pair(&pa, &ta, stream))) return rc;
       ref_rows = zr;
       ref_ld = p.ld;
-    } else if (p.needs_ref) {
+    } else if ((rc = clear_head_project(&pa, stream))) {
+      return rc;
+    }
+    if (!p.project_teacher && p.needs_ref) {
       ref_rows = static_cast<const uint8_t*>(a->ref_logits) + r0 * a->ref_logits_ld * ref_esz;
       ref_ld = a->ref_logits_ld;
       ref_f32 = a->ref_logits_f32 ? 1 : 0;

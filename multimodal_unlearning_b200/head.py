@@ -124,6 +124,19 @@ def project(hidden: torch.Tensor, weight: torch.Tensor, logits: torch.Tensor, ls
     _timed("gemm_project", lambda: _lib.check(lib.clear_head_project(C.byref(a), _stream()), "clear_head_project"))
 
 
+def project_pair(hidden, weight, logits, lse_part, ref_hidden, ref_weight, ref_logits, ref_lse_part, cta_group: int = 0) -> None:
+    """Student and teacher projections of the same rows as ONE launch (clear_head_project_pair)."""
+    lib = _lib.load()
+
+    def args(hd, w, z, part):
+        return _lib.ProjectArgs(hidden=hd.data_ptr(), weight=w.data_ptr(), logits=z.data_ptr(), lse_part=part.data_ptr(),
+                                hidden_ld=hd.stride(0), weight_ld=w.stride(0), logits_ld=z.stride(0), n_rows=hd.shape[0],
+                                hidden_dim=hd.shape[1], vocab=w.shape[0], cta_group=cta_group)
+
+    a, b = args(hidden, weight, logits, lse_part), args(ref_hidden, ref_weight, ref_logits, ref_lse_part)
+    _timed("gemm_project_pair", lambda: _lib.check(lib.clear_head_project_pair(C.byref(a), C.byref(b), _stream()), "clear_head_project_pair"))
+
+
 def rowloss(kind: int, logits: torch.Tensor, lse_part: torch.Tensor, loss_rows: torch.Tensor, vocab: int, *,
             ref_logits: torch.Tensor | None = None, ref_lse_part: torch.Tensor | None = None,
             labels: torch.Tensor | None = None, row_weight: torch.Tensor | None = None,
@@ -160,16 +173,9 @@ def backward(dlogits: torch.Tensor, vocab: int, hidden: torch.Tensor, weight: to
         for r, ptr in enumerate(dweight_peers):
             a.dweight_peers[r] = ptr
         dweight = True  # a dW contraction is requested (its output goes to the peers' buffers)
-    if StageTimer.active is None or dhidden is None or dweight is None:
-        tag = "gemm_dweight" if dhidden is None else ("gemm_dhidden" if dweight is None else "gemm_backward")
-        _timed(tag, lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
-        return
-    # timed runs issue the two contractions separately so that each launch gets its own events
-    n_peers, dw_ptr = a.n_peers, a.dweight
-    a.dweight, a.n_peers = None, 0
-    _timed("gemm_dhidden", lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
-    a.dweight, a.n_peers, a.dhidden = dw_ptr, n_peers, None
-    _timed("gemm_dweight", lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
+    # dH and dW together are ONE launch when both are bf16 (csrc/head.cu: clear_head_backward)
+    tag = "gemm_dweight" if dhidden is None else ("gemm_dhidden" if dweight is None else "gemm_backward")
+    _timed(tag, lambda: _lib.check(lib.clear_head_backward(C.byref(a), _stream()), "clear_head_backward"))
 
 
 def count_valid(labels: torch.Tensor, inv_count: torch.Tensor) -> None:
@@ -402,9 +408,17 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         else:
             dweight = torch.empty(weight.shape, dtype=torch.float32, device=dev)
 
-    launches += n_blocks * (2 + int(needs_ref) + (int(need_dhidden) + int(need_dweight) if write_grad else 0)) + 1 + int(bool(n_seqs))
-    if compact_ignored:   # compact, gather labels (+ row weights), gather hidden, scatter loss terms (+ dH); per block: zero + convert of dH
-        launches += 4 + int(row_weight is not None) + int(row_index is not None) + int(need_dhidden) * (1 + 2 * n_blocks)
+    paired_proj = needs_ref and ref_logits is None                      # student + teacher projection: one launch
+    dw_f32 = need_dweight and (dweight_accum is not None or (peers is None and dweight is not None and dweight.dtype == torch.float32))
+    # dH + dW: one launch when both are bf16 and dH alone would starve its last wave (small blocks, compacted rows); the
+    # count below assumes the starved case for blocks under 8192 rows and compaction — it is the library that decides
+    paired_bwd = need_dhidden and need_dweight and not dw_f32 and (compact_ignored or blk < 8192)
+    n_bwd = 0 if not write_grad else (1 if paired_bwd else int(need_dhidden) + int(need_dweight))
+    launches += n_blocks * (2 + int(needs_ref and not paired_proj) + n_bwd) + 1 + int(bool(n_seqs))
+    if compact_ignored:   # compact, gather labels (+ row weights), gather hidden, scatter loss terms (+ dH); a dH contraction on its
+        # own (fp32 dW beside it, or no dW) runs over an fp32 scratch: zero + convert per block
+        launches += (4 + int(row_weight is not None) + int(row_index is not None)
+                     + int(need_dhidden) * (1 + (0 if paired_bwd else 2 * n_blocks)))
     elif row_index is not None:
         launches += 1 + int(needs_ref and ref_logits is None) + int(need_dhidden)
     if one_call:
@@ -465,6 +479,10 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         else:
             _ref_lse(ref_logits[r0:r1], rpart[: r1 - r0], v)
 
+    def do_project_both(b):   # student + teacher projection: one launch
+        r0, r1, zb, pb = block(b)
+        project_pair(hidden[r0:r1], weight, zb, pb, ref_hidden[r0:r1], ref_weight, zr[: r1 - r0], rpart[: r1 - r0], cta_group)
+
     def do_rowloss(b):
         r0, r1, zb, pb = block(b)
         zrb = rpb = None
@@ -486,9 +504,12 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
 
     if not pipelined:
         for b in range(n_blocks):
-            do_project(b)
-            if needs_ref:
-                do_teacher(b)
+            if needs_ref and ref_logits is None:
+                do_project_both(b)
+            else:
+                do_project(b)
+                if needs_ref:
+                    do_teacher(b)
             do_rowloss(b)
             if write_grad:
                 do_backward(b)

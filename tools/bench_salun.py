@@ -80,6 +80,16 @@ def run(layers=32, reps=3, peak_gbs=6525.2, adam=True):
         b = 22.125
         out["masked_adamw(packed mask, fused clip)"] = {"ms": ms, "bytes_per_param": b, "gbs": b * P / ms / 1e6,
                                                         "frac": b * P / ms / 1e6 / peak_gbs}
+        del m, v
+        torch.cuda.empty_cache()
+        s1, s2, a1, a2 = salun.adamw8_init(P, dev)
+        salun.masked_adamw8_flat(param, grads, s1, s2, a1, a2, bits, 1, grad_scale=coef)     # states away from zero
+        ms = timed(lambda: salun.masked_adamw8_flat(param, grads, s1, s2, a1, a2, bits, 2, grad_scale=coef))
+        b = 2 + 2 + 2 + 1 + 1 + 1 + 1 + 0.125 + 4 * 4 / 256     # p r/w, g, two 8-bit states r/w, packed mask, two absmax r/w per 256
+        out["masked_adamw_8bit_states(packed mask, fused clip)"] = {"ms": ms, "bytes_per_param": b, "gbs": b * P / ms / 1e6,
+                                                                    "frac": b * P / ms / 1e6 / peak_gbs,
+                                                                    "optimizer_state_bytes_per_param": 2 + 8 / 256}
+        del s1, s2, a1, a2
         ms = timed(lambda: norms.param_l1l0([param], [grads]))
         out["param_l1l0(vs reference params)"] = {"ms": ms, "bytes_per_param": 4, "gbs": 4 * P / ms / 1e6, "frac": 4 * P / ms / 1e6 / peak_gbs}
     return out
