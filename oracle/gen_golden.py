@@ -271,11 +271,31 @@ def gen_row_map():
     print("row_map: seq_loss", loss.detach().tolist())
 
 
+def gen_legacy_dpo():
+    """The UNMODIFIED `MMTrainerForgetting.compute_loss` with loss_type "dpo" on the legacy-processor stand-in
+    (ref_harness.LegacyExpandLM: T' = L + 575 rows per sample), i.e. through the reference's own remove_image_tokens /
+    get_batch_loss calls (mm/trainer.py:364-398): the loss and the gradients it leaves on the model."""
+    MM, _, _, _ = RH.import_reference()
+    student, teacher = RH.LegacyExpandLM(0), RH.LegacyExpandLM(1)
+    inputs = {"retain": RH.legacy_split(4, 40, 1), "idk": RH.legacy_split(4, 40, 2), "forget": RH.legacy_split(4, 40, 3)}
+    fake = types.SimpleNamespace(loss_type="dpo", teacher_model=teacher, loss_beta=1.0, l1_lambda=0.0, l0_lambda=0.0,
+                                 l_norm_from="zero", loss_args={}, is_deepspeed_enabled=False,
+                                 to_device=MM.MMTrainerForgetting.to_device)
+    loss = MM.MMTrainerForgetting.compute_loss(fake, student, inputs)
+    loss.backward()
+    out = {"loss": loss.detach().double().numpy()}
+    for n, p in student.named_parameters():
+        out[f"grad::{n}"] = p.grad.float().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+    np.savez_compressed(GOLDEN / "legacy_dpo.npz", **out)
+    print("legacy_dpo: loss", float(loss))
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     which = set(sys.argv[1:]) or {"mm", "nlp", "salun", "reg", "row_map"}
     if "row_map" in which:
         gen_row_map()
+        gen_legacy_dpo()
     if "reg" in which:
         gen_regulariser()
     if "mm" in which:

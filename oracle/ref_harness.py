@@ -265,3 +265,59 @@ def run_mm_dpo_true(student, teacher, inputs: dict):
         "dweight": student.lm_head.weight.grad.detach().clone(),
     }
 
+
+
+# --------------------------------------------------------------------------------------------------
+# A LLaVA checkpoint as a LEGACY processor drives it (transformers 4.45.1, the reference's pin): input_ids carry ONE image
+# placeholder per sample and the model expands it into 576 patch rows inside forward, so the logits have T' = L + 575 rows
+# and `dpo` crops them with remove_image_tokens (mm/trainer.py:373-387).  transformers 5.x pre-expands the placeholders, so
+# the tiny-LLaVA fixtures never take that branch; this stand-in does, with the reference's own assumptions (at most one
+# image per sample, samples without an image left-padded to the common length).
+# --------------------------------------------------------------------------------------------------
+LEGACY_VOCAB, LEGACY_HIDDEN, LEGACY_PATCHES, LEGACY_IMAGE_TOKEN = 1000, 64, 576, 999
+
+
+class LegacyExpandLM(torch.nn.Module):
+    def __init__(self, seed: int = 0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.config = types.SimpleNamespace(image_token_index=LEGACY_IMAGE_TOKEN, tie_word_embeddings=False)
+        self.embed = torch.nn.Embedding(LEGACY_VOCAB, LEGACY_HIDDEN)
+        self.patch = torch.nn.Parameter(torch.empty(LEGACY_PATCHES, LEGACY_HIDDEN))
+        self.mix = torch.nn.Linear(LEGACY_HIDDEN, LEGACY_HIDDEN)
+        self.lm_head = torch.nn.Linear(LEGACY_HIDDEN, LEGACY_VOCAB, bias=False)
+        with torch.no_grad():
+            self.embed.weight.copy_(torch.randn(LEGACY_VOCAB, LEGACY_HIDDEN, generator=g))
+            self.patch.copy_(0.5 * torch.randn(LEGACY_PATCHES, LEGACY_HIDDEN, generator=g))
+            self.mix.weight.copy_(torch.randn(LEGACY_HIDDEN, LEGACY_HIDDEN, generator=g) / LEGACY_HIDDEN ** 0.5)
+            self.mix.bias.zero_()
+            self.lm_head.weight.copy_(0.2 * torch.randn(LEGACY_VOCAB, LEGACY_HIDDEN, generator=g))
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def forward(self, input_ids, attention_mask=None, labels=None, pixel_values=None):
+        x = self.embed(input_ids)
+        rows = []
+        for i in range(input_ids.shape[0]):
+            pos = (input_ids[i] == LEGACY_IMAGE_TOKEN).nonzero().flatten()
+            if pos.numel() == 0:   # no image: left padding up to the common length
+                rows.append(torch.cat([x.new_zeros(LEGACY_PATCHES - 1, x.shape[-1]), x[i]]))
+            else:
+                s0 = int(pos[0])
+                rows.append(torch.cat([x[i, :s0], self.patch.to(x.dtype), x[i, s0 + 1:]]))
+        h = torch.tanh(self.mix(torch.stack(rows)))
+        return types.SimpleNamespace(logits=self.lm_head(h), loss=None)
+
+
+def legacy_split(batch: int, length: int, seed: int, image_at=(5, 0, None, 30)):
+    """{input_ids, attention_mask, labels} with one image placeholder per sample at `image_at[i]` (None: text only)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, LEGACY_IMAGE_TOKEN - 50, (batch, length), generator=g)
+    for i in range(batch):
+        at = image_at[i % len(image_at)]
+        if at is not None:
+            ids[i, at] = LEGACY_IMAGE_TOKEN
+    labels = torch.randint(0, LEGACY_VOCAB, (batch, length), generator=g)
+    labels[:, : length - 8] = -100
+    return {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels}

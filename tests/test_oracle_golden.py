@@ -262,3 +262,30 @@ def test_adamw8_oracle_properties():
     assert torch.equal(p8, p32)                                   # the states are quantised AFTER the update: step 1 is exact
     m8 = SO.dynamic_map(True)[s1] * np.repeat(a1, 256)
     assert np.abs(m8 - m).max() <= 0.02 * np.abs(m).max()
+
+
+def test_oracle_dpo_on_the_legacy_processor_fixture():
+    """tests/golden/legacy_dpo.npz: the unmodified reference `compute_loss("dpo")` on a model that expands the image placeholder
+    itself (T' = L + 575).  The oracle's `dpo` on the rows the reference's remove_image_tokens keeps gives the same loss and
+    the same lm_head gradient."""
+    z = np.load(GOLDEN / "legacy_dpo.npz")
+    model = RH.LegacyExpandLM(0)
+    idk = RH.legacy_split(4, 40, 2)
+    captured = {}
+    hook = model.lm_head.register_forward_pre_hook(lambda m, args: captured.__setitem__("h", args[0]))
+    model(**idk)
+    hook.remove()
+    hidden = captured["h"].detach()                                       # [B, T', H]
+    b, tp, h = hidden.shape
+    l = idk["input_ids"].shape[1]
+    rows = []
+    for i in range(b):                                                     # remove_image_tokens as an index (mm/trainer_utils.py:48-70)
+        pos = (idk["input_ids"][i] == RH.LEGACY_IMAGE_TOKEN).nonzero().flatten()
+        s0 = int(pos[0]) if pos.numel() else 0
+        rows.append(torch.cat([torch.arange(s0), torch.arange(tp - (l - s0), tp)]))
+    cropped = torch.stack([hidden[i, r] for i, r in enumerate(rows)])
+    w = model.lm_head.weight.detach()
+    loss, dh, dw = HO.loss_and_grads(HO.mm_compute_loss, {"idk": HO.HeadInputs(cropped, idk["labels"])}, w, loss_type="dpo")
+    assert abs(loss.item() - float(z["loss"])) <= 2e-5 * abs(float(z["loss"]))
+    want_dw = torch.from_numpy(z["grad::lm_head.weight"])
+    assert ((dw - want_dw).norm() / want_dw.norm()).item() <= 2e-4

@@ -214,3 +214,54 @@ def test_teacher_cache_replays_the_same_loss_without_teacher_forwards(kind, loss
     assert counter.n > before
     assert changed.item() == call(mk(0), other).item()
     counter.h.remove()
+
+
+def test_mm_dpo_with_a_legacy_processor_against_the_reference_fixture():
+    """A6d end to end: `dpo` on a model that expands the image placeholder inside forward (legacy processor, T' = L + 575
+    rows).  tests/golden/legacy_dpo.npz holds the loss and every parameter gradient of the UNMODIFIED reference trainer
+    (remove_image_tokens + get_batch_loss on [B, T', V] logits, fp32, CPU); here the trunk's hidden rows are selected by the
+    fused head's row_index input (compacted to the labelled rows on the device) — no cropped copy of logits or hidden."""
+    import numpy as np
+
+    from multimodal_unlearning_b200 import trainer as T
+    from tests._golden import GOLDEN
+    dev = torch.device("cuda:0")
+    z = np.load(GOLDEN / "legacy_dpo.npz")
+    student, teacher = RH.LegacyExpandLM(0).to(dev), RH.LegacyExpandLM(1).to(dev)
+    inputs = {"retain": RH.legacy_split(4, 40, 1), "idk": RH.legacy_split(4, 40, 2), "forget": RH.legacy_split(4, 40, 3)}
+    fake = types.SimpleNamespace(loss_type="dpo", teacher_model=teacher, loss_beta=1.0, l1_lambda=0.0, l0_lambda=0.0,
+                                 l_norm_from="zero", loss_args={})
+    loss = T.MMTrainerForgetting.compute_loss(fake, student, inputs)
+    loss.backward()
+    want = float(z["loss"])
+    assert abs(loss.item() - want) <= 2e-3 * abs(want), (loss.item(), want)
+    for n, p in student.named_parameters():
+        w = torch.from_numpy(z[f"grad::{n}"])
+        g = p.grad.detach().float().cpu()
+        rel = ((g - w).norm() / w.norm().clamp_min(1e-30)).item()
+        assert rel <= 3e-2, (n, rel)                       # the head runs in bf16 (logits, dlogits), the reference in fp32
+    assert type(student.lm_head).__name__ == "Linear"
+    # the flagged sigmoid log-ratio takes the same four row maps (student / teacher x idk / forget)
+    student.zero_grad(set_to_none=True)
+    fake.dpo_true = True
+    lt = T.MMTrainerForgetting.compute_loss(fake, student, inputs)
+    lt.backward()
+    assert torch.isfinite(lt) and all(torch.isfinite(p.grad).all() for p in student.parameters())
+    # CE recipes on the same model: labels follow their tokens onto the expanded rows, image rows are ignored
+    student.zero_grad(set_to_none=True)
+    fake.dpo_true, fake.loss_type = False, "grad_ascent"
+    got = T.MMTrainerForgetting.compute_loss(fake, student, inputs)
+    f = {k: v.to(dev) for k, v in inputs["forget"].items()}
+    logits = student(**f).logits.float()
+    tp, l = logits.shape[1], f["input_ids"].shape[1]
+    exp = torch.full((f["input_ids"].shape[0], tp), -100, dtype=torch.long, device=dev)
+    for i in range(exp.shape[0]):
+        pos = (f["input_ids"][i] == RH.LEGACY_IMAGE_TOKEN).nonzero().flatten()
+        if pos.numel() == 0:
+            exp[i, tp - l:] = f["labels"][i]
+        else:
+            s0 = int(pos[0])
+            exp[i, :s0] = f["labels"][i, :s0]
+            exp[i, s0 + RH.LEGACY_PATCHES:] = f["labels"][i, s0 + 1:]
+    want_ce = -torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), exp[:, 1:].reshape(-1), ignore_index=-100)
+    assert abs(got.item() - want_ce.item()) <= 2e-3 * abs(want_ce.item()), (got.item(), want_ce.item())

@@ -1,12 +1,21 @@
 #!/bin/bash
-# Everything the round's profiles/ are made from, in one gpurun call (1 GPU).  Outputs under gpurun_out/.
+# Everything the round's profiles/ are made from, in one gpurun call (1 GPU).  Outputs under gpurun_out/ (prefix r02f_).
 set -u
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
-python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 400 gpurun_out/bench_final.json; echo
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-python tools/bench_configs.py > gpurun_out/configs_bench.log 2>&1; tail -1 gpurun_out/configs_bench.log | cut -c1-200
-python tools/bench_salun.py --reps 3 > gpurun_out/salun_bench.log 2>&1
-bash tools/ncu_round.sh > gpurun_out/ncu_round.log 2>&1
-bash tools/ncu_salun.sh > gpurun_out/ncu_salun_round.log 2>&1
-ls gpurun_out | head -80
+O=gpurun_out
+python -m pytest tests -m gpu -q > $O/r02f_pytest_gpu.log 2>&1; tail -2 $O/r02f_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/r02f_smoke.log 2>&1; tail -1 $O/r02f_smoke.log
+python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/r02f_bench_ref.json 2> $O/r02f_bench_ref.err
+python bench.py --gpus 1 --steps 20 --warmup 5 > $O/r02f_bench.json 2> $O/r02f_bench.err; tail -c 300 $O/r02f_bench.json; echo
+for c in 3 4 5; do python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-salun --no-extras --config $c > $O/r02f_cfg$c.json 2> $O/r02f_cfg$c.err; done
+python tools/bench_configs.py > $O/r02f_configs.log 2>&1; cp $O/configs_bench.md $O/r02f_configs.md 2>/dev/null
+python tools/gpu_block_ab.py 8192,4096,2048,1024 > $O/r02f_block_ab.log 2>&1
+# ncu: launch list of the bench command, then one full capture of the hot kernels (each only after the plain run exited 0)
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-salun --no-extras"
+$CMD > $O/r02f_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02f_bench_launches.csv $CMD > $O/r02f_ncu_list.log 2>&1
+$CMD > $O/r02f_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'gemm_bf16|rowloss' -s 22 -c 8 -o $O/r02f_prof $CMD > $O/r02f_ncu_full.log 2>&1
+SAL="python tools/bench_salun.py --layers 4 --reps 1"
+$SAL > $O/r02f_salun_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'histogram_kernel|hist_total|select_global|mask_kernel|adamw_kernel|adamw8_kernel|sqnorm_kernel|l1l0_kernel|accumulate_kernel' -c 30 -o $O/r02f_prof_salun $SAL > $O/r02f_ncu_salun.log 2>&1
+ls -la $O | grep r02f_ | awk '{print $5, $9}'
