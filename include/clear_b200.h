@@ -374,10 +374,11 @@ int clear_masked_adamw(const ClearAdamWArgs* args, void* stream);
  * computes).  Both moments are one byte per parameter: an index into a 256-entry sorted codebook (code1 signed for exp_avg,
  * code2 non-negative for exp_avg_sq; host-generated "dynamic" maps) times one fp32 absmax per block of
  * clear_adamw8_block_elems() = 256 parameters (absmax1 / absmax2: ceil(n / 256) floats each).  One fused pass: dequantise ->
- * the update of clear_masked_adamw (same operation order) -> new block absmax -> requantise; quantisation = #{fp32 midpoints of
- * neighbouring code entries that are < x / absmax}.  qlut1 (65536 bytes) / qlut2 (32768 bytes): for every top-16-bit pattern of
- * the order-preserving float key (qlut2: of the non-negative floats) a lower bound of that count (any lower bound is
- * correct; a tight one is fast).  States start as the index of 0.0 with absmax 0. */
+ * the update of clear_masked_adamw (same operation order) -> new block absmax -> requantise.  Quantisation of x: n = x * (1 /
+ * absmax) (IEEE reciprocal, one multiply; 0 for an all-zero block), key = (bits(n) + 0x8000) >> 16 (n rounded to sign, exponent
+ * and 7 mantissa bits), index = qlut[key].  qlut1 (65536 bytes, every 16-bit pattern) / qlut2 (32768 bytes, the non-negative
+ * ones): the index of the code value nearest to the float whose top 16 bits are the key (host-generated from the codebooks:
+ * #{fp32 midpoints of neighbouring code values that are < it}).  States start as the index of 0.0 with absmax 0. */
 typedef struct ClearAdamW8Args {
   void* param;            /* bf16 [n] */
   const void* grad;       /* bf16 [n] */

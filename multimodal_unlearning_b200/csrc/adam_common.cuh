@@ -30,6 +30,20 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
   return __fsub_rn(p, __fmul_rn(c.step_size, q));   // addcdiv_(exp_avg, denom, -step_size)
 }
 
+// The update of the 8-bit-state kernel.  Same quantities, but the two divisions are spelled as multiplications by exactly
+// rounded reciprocals (x / bc2_sqrt -> x * fp32(1 / bc2_sqrt), m / denom -> m * (1 / denom)): an IEEE division costs ~10
+// instructions with its slow-path check, and this kernel is issue-bound, not HBM-bound (10 bytes per parameter).  The result
+// differs from adam_one's in the last bit now and then — far below the 8-bit resolution of the states it is stored in; the
+// oracle (oracle/salun_oracle.py::adamw8_step) restates exactly this sequence.
+__device__ __forceinline__ float adam8_one(float p, float g, float& m, float& v, const AdamConsts& c, float inv_bc2_sqrt) {
+  p = __fmul_rn(p, c.decay);
+  m = __fadd_rn(m, __fmul_rn(c.w1, __fsub_rn(g, m)));
+  v = __fadd_rn(__fmul_rn(v, c.beta2), __fmul_rn(c.w2, __fmul_rn(g, g)));
+  const float sq = (v == 0.f) ? v : __fsqrt_rn((v == 0.f) ? 1.f : v);   // sqrt(+0) takes the slow path: masked-out parameters stay at zero forever
+  const float denom = __fadd_rn(__fmul_rn(sq, inv_bc2_sqrt), c.eps);
+  return __fsub_rn(p, __fmul_rn(c.step_size, __fmul_rn(m, __frcp_rn(denom))));
+}
+
 // Scalar prologue of torch.optim.adam._single_tensor_adam, in double like the Python floats there.
 inline AdamConsts make_adam_consts(double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                                    const float* grad_scale_dev) {

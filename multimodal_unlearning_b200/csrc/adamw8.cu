@@ -8,14 +8,15 @@
 // (parity unpinned; the oracle restates exactly what is computed here, oracle/salun_oracle.py::adamw8_step):
 //   * block = 256 parameters = the 8 consecutive elements of each of a warp's 32 lanes: the block absmax is a warp
 //     shuffle reduction, no shared memory, no second pass;
-//   * one fused pass: dequantise m, v (codebook lookup x block absmax) -> masked, optionally clipped gradient -> the same
-//     fp32 update as the fp32-state kernel (adam_common.cuh, torch's _single_tensor_adam operation order) -> new block
-//     absmax -> requantise -> store; 10.2 bytes of HBM traffic per parameter instead of 22.1;
-//   * quantisation = index of the nearest codebook entry of x / absmax, defined as #{midpoints < x} over the fp32
-//     midpoints of neighbouring entries.  A binary search costs 8 dependent shared-memory loads per state and element
-//     and would make the pass issue-bound; instead a 65536-entry table indexed by the top 16 bits of the (order-
-//     preserving) float pattern gives a lower bound that is at most a step or two away, finished by comparing against
-//     the midpoints themselves — the result is exactly the definition's, whatever the table's resolution.
+//   * one fused pass: dequantise m, v (codebook lookup x block absmax) -> masked, optionally clipped gradient -> the AdamW
+//     update in fp32 (adam_common.cuh::adam8_one: torch's quantities, divisions spelled as reciprocal multiplies) -> new
+//     block absmax -> requantise -> store; 10.2 bytes of HBM traffic per parameter instead of 22.1;
+//   * quantisation = the nearest codebook entry of x * (1 / absmax) ROUNDED TO ITS TOP 16 BITS (sign, exponent, 7 mantissa
+//     bits: key = (bits + 0x8000) >> 16, round half away from zero — unbiased, and 0.4 % of the value at most, below the
+//     1.4 % spacing of the finest codes), which makes the quantiser ONE byte load from a 65536-entry (signed) / 32768-entry
+//     (unsigned) table in shared memory: no binary search (8 dependent loads per state and element), no data-dependent
+//     loop, no divergence.  A first version searched the exact midpoints from a table lower bound: 58.9 ms per step over
+//     6.74 B parameters (LSU- and branch-bound); this one is bound by the exact IEEE division / square root of the update.
 #include <cuda_bf16.h>
 
 #include "adam_common.cuh"
@@ -28,7 +29,7 @@ constexpr int kBlock = 256;       // parameters per absmax block (one warp x 8 e
 constexpr int kThreads = 512;     // x 2 CTAs per SM (98 KB of tables each): 1024 threads, 48 KB of loads in flight per SM
 constexpr int kLut1 = 65536;      // signed codebook: every top-16-bit float pattern
 constexpr int kLut2 = 32768;      // unsigned codebook: the non-negative half
-constexpr int kSmemBytes = kLut1 + kLut2 + 4 * 256 * 4;   // + code1, code2, mid1, mid2
+constexpr int kSmemBytes = kLut1 + kLut2 + 2 * 256 * 4;   // + code1, code2
 
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   uint4 r;
@@ -36,17 +37,10 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   return r;
 }
 
-// order-preserving map float -> uint32, top 16 bits
-__device__ __forceinline__ uint32_t key16(float a) {
-  const uint32_t b = __float_as_uint(a);
-  return (b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u)) >> 16;
-}
-
-// #{i < 255 : mid[i] < a}, starting from the table's lower bound
-__device__ __forceinline__ uint32_t quantise(float a, const uint8_t* lut, uint32_t key, const float* mid) {
-  uint32_t i = lut[key];
-  while (i < 255u && mid[i] < a) ++i;
-  return i;
+// index of the nearest code value of `a` rounded to its top 16 bits (see the header comment); `mask` = 0xFFFF (signed table
+// over all patterns) or 0x7FFF (unsigned table: a >= 0)
+__device__ __forceinline__ uint32_t quantise(float a, const uint8_t* lut, uint32_t mask) {
+  return lut[((__float_as_uint(a) + 0x8000u) >> 16) & mask];
 }
 
 struct Adam8Params {
@@ -65,22 +59,18 @@ struct Adam8Params {
 };
 
 template <bool kPackedMask>
-__global__ void __launch_bounds__(kThreads, 2) adamw8_kernel(const Adam8Params a, const AdamConsts c) {
+__global__ void __launch_bounds__(kThreads, 2) adamw8_kernel(const Adam8Params a, const AdamConsts c, const float inv_bc2_sqrt) {
   extern __shared__ uint8_t smem[];
   uint8_t* lut1 = smem;
   uint8_t* lut2 = smem + kLut1;
   float* code1 = reinterpret_cast<float*>(smem + kLut1 + kLut2);
   float* code2 = code1 + 256;
-  float* mid1 = code2 + 256;
-  float* mid2 = mid1 + 256;
   for (int i = threadIdx.x; i < kLut1 / 16; i += kThreads) reinterpret_cast<uint4*>(lut1)[i] = reinterpret_cast<const uint4*>(a.lut1)[i];
   for (int i = threadIdx.x; i < kLut2 / 16; i += kThreads) reinterpret_cast<uint4*>(lut2)[i] = reinterpret_cast<const uint4*>(a.lut2)[i];
   if (threadIdx.x < 256) {
     const int i = threadIdx.x;
     code1[i] = a.code1[i];
     code2[i] = a.code2[i];
-    mid1[i] = (i < 255) ? __fmul_rn(__fadd_rn(a.code1[i], a.code1[i + 1]), 0.5f) : INFINITY;
-    mid2[i] = (i < 255) ? __fmul_rn(__fadd_rn(a.code2[i], a.code2[i + 1]), 0.5f) : INFINITY;
   }
   __syncthreads();
   const float gscale = c.grad_scale ? *c.grad_scale : 1.f;
@@ -142,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 2) adamw8_kernel(const Adam8Params a
       if (j < live) {
         float gj = ((mk >> j) & 1u) ? g[j] : 0.f;                                                    // grad *= mask
         if (c.grad_scale) gj = __bfloat162float(__float2bfloat16_rn(__fmul_rn(gj, gscale)));        // grad.mul_(clip_coef) in bf16
-        p[j] = adam_one(p[j], gj, m[j], v[j], c);
+        p[j] = adam8_one(p[j], gj, m[j], v[j], c, inv_bc2_sqrt);
         mx1 = fmaxf(mx1, fabsf(m[j]));
         mx2 = fmaxf(mx2, v[j]);
       }
@@ -152,13 +142,13 @@ __global__ void __launch_bounds__(kThreads, 2) adamw8_kernel(const Adam8Params a
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
       mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
     }
+    const float inv1 = (mx1 > 0.f) ? __frcp_rn(mx1) : 0.f;   // one IEEE reciprocal per block and state, then a multiply per element
+    const float inv2 = (mx2 > 0.f) ? __frcp_rn(mx2) : 0.f;
     uint32_t q1[8], q2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float n1 = (mx1 > 0.f) ? __fdiv_rn(m[j], mx1) : 0.f;
-      const float n2 = (mx2 > 0.f) ? __fdiv_rn(v[j], mx2) : 0.f;
-      q1[j] = quantise(n1, lut1, key16(n1), mid1);
-      q2[j] = quantise(n2, lut2, key16(n2) & 0x7FFFu, mid2);   // n2 >= 0: the key's top bit is set
+      q1[j] = quantise(__fmul_rn(m[j], inv1), lut1, 0xFFFFu);
+      q2[j] = quantise(__fmul_rn(v[j], inv2), lut2, 0x7FFFu);
     }
     if (live == 8) {
       uint4 pr;
@@ -206,6 +196,7 @@ int clear_masked_adamw_8bit(const ClearAdamW8Args* a, void* stream) {
   if (a->mask && (reinterpret_cast<uintptr_t>(a->mask) & 7)) return fail(CLEAR_ERR_ALIGN, "clear_masked_adamw_8bit: mask must be 8-byte aligned");
   if (a->mask && a->mask_bits) return fail(CLEAR_ERR_KIND, "clear_masked_adamw_8bit: pass mask or mask_bits, not both");
   const AdamConsts c = make_adam_consts(a->lr, a->beta1, a->beta2, a->eps, a->weight_decay, a->step, a->grad_scale_dev);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(a->beta2, (double)a->step)));
   Adam8Params p;
   p.param = static_cast<__nv_bfloat16*>(a->param);
   p.grad = static_cast<const __nv_bfloat16*>(a->grad);
@@ -222,10 +213,10 @@ int clear_masked_adamw_8bit(const ClearAdamW8Args* a, void* stream) {
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   if (a->mask_bits) {
     CLEAR_CUDA_OK(cudaFuncSetAttribute(adamw8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    adamw8_kernel<true><<<(unsigned)blocks, kThreads, kSmemBytes, cs>>>(p, c);
+    adamw8_kernel<true><<<(unsigned)blocks, kThreads, kSmemBytes, cs>>>(p, c, inv_bc2_sqrt);
   } else {
     CLEAR_CUDA_OK(cudaFuncSetAttribute(adamw8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    adamw8_kernel<false><<<(unsigned)blocks, kThreads, kSmemBytes, cs>>>(p, c);
+    adamw8_kernel<false><<<(unsigned)blocks, kThreads, kSmemBytes, cs>>>(p, c, inv_bc2_sqrt);
   }
   CLEAR_CUDA_OK(cudaGetLastError());
   return 0;

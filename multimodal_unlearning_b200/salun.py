@@ -397,18 +397,13 @@ def dynamic_codebook(signed: bool) -> torch.Tensor:
 
 
 def quantisation_tables(code: torch.Tensor, signed: bool) -> torch.Tensor:
-    """uint8 lower-bound table of the kernel's quantiser: for every top-16-bit pattern of the order-preserving float key
-    (signed: all 65536; unsigned: the 32768 non-negative ones) the number of code midpoints below the SMALLEST float with that
-    pattern — a lower bound of the index of any float of the bucket, which the kernel finishes by comparing midpoints."""
+    """uint8 table of the kernel's quantiser: for every 16-bit pattern (sign, exponent, 7 mantissa bits; unsigned codebook:
+    the 32768 non-negative ones) the index of the code value nearest to the float `pattern << 16` — the number of fp32
+    midpoints of neighbouring code values below it.  The kernel rounds x / absmax to its top 16 bits and looks the index up."""
     mid = ((code[:-1] + code[1:]) * 0.5).to(torch.float32)
-    if signed:
-        u = torch.arange(65536, dtype=torch.int64) << 16                       # smallest sortable key of the bucket
-        bits = torch.where(u >= 0x80000000, u ^ 0x80000000, (~u) & 0xFFFFFFFF)   # back to the IEEE pattern
-        # a negative float's bucket: its smallest member has all low key bits 0, i.e. all low pattern bits 1
-    else:
-        bits = torch.arange(32768, dtype=torch.int64) << 16
+    bits = torch.arange(65536 if signed else 32768, dtype=torch.int64) << 16
     x = torch.where(bits >= 0x80000000, bits - (1 << 32), bits).to(torch.int32).view(torch.float32)
-    x = torch.nan_to_num(x, nan=-float("inf") if signed else 0.0)
+    x = torch.nan_to_num(x, nan=0.0)                 # NaN patterns never occur (|x / absmax| <= 1)
     return torch.searchsorted(mid, x.contiguous(), right=False).to(torch.uint8)
 
 

@@ -259,7 +259,10 @@ def test_adamw8_oracle_properties():
     a1, a2 = np.zeros(8, np.float32), np.zeros(8, np.float32)
     p8, s1, s2, a1, a2 = SO.adamw8_step(p, gr, s1, s2, a1, a2, None, 1, lr=1e-3)
     p32, m, v = SO.adamw_step(p, gr, np.zeros(n, np.float32), np.zeros(n, np.float32), None, 1, lr=1e-3)
-    assert torch.equal(p8, p32)                                   # the states are quantised AFTER the update: step 1 is exact
+    # the states are quantised AFTER the update, so step 1 differs from the fp32-state step only through the reciprocal-multiply
+    # spelling of the two divisions: at most the last bf16 bit of a parameter
+    assert (p8.view(torch.int16).int() - p32.view(torch.int16).int()).abs().max().item() <= 1
+    assert (p8 != p32).float().mean().item() <= 0.02
     m8 = SO.dynamic_map(True)[s1] * np.repeat(a1, 256)
     assert np.abs(m8 - m).max() <= 0.02 * np.abs(m).max()
 
