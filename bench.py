@@ -11,9 +11,10 @@ micro-batch (weak scaling) and dW is averaged over ranks by the all-reduce fused
 grad_ascent bs 16 x seq 512) with the same JSON contract, so the 1/2/4/8-GPU runs of configs[4] can be reproduced.
 Prints ONE JSON line (rank 0).
 
-`value`    device-resident inputs, CUDA-event timed, max over ranks; timed with per-launch CUDA events around every
-           kernel stage (they feed `roofline`).  `value_one_call` is the same step through the one-call C entry
-           (clear_head_loss_fwd_bwd, what the trainers run) without the per-launch events.
+`value`    device-resident inputs, CUDA-event timed, max over ranks; every step runs the one-call C entry
+           (clear_head_loss_fwd_bwd: what the trainers run) and the LIBRARY records CUDA events between its stages
+           (ClearHeadArgs.stage_events: projection(s) / row pass / backward contractions), which feed `roofline`.
+           `value_one_call` is the same loop without those events (a cross-check: the events cost nothing).
 `e2e`      the same step through the public API with HOST (pinned) inputs: every step copies the hidden states, the
            teacher's hidden states and the labels host->device and reads the loss back (copies double-buffered on a side
            stream; all of them inside the timed region).
@@ -100,7 +101,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", os.environ.get("CLEAR_BENCH_SMI_MS", "20"), "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -540,35 +541,49 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # nvidia-smi needs a moment to start: launched before the warm-up, marked at the timed region
-    # warm-up in the mode the timed region runs in (per-launch events: the staged entry points, their own allocations), then
-    # once through the one-call entry; the events of the warm-up are discarded
-    with head.StageTimer():
-        for i in range(max(3, args.warmup)):
-            res = step(i, dev_in)
-    drain()
-    barrier()
-    launches_per_step = res.launches * (2 if multi_split else 1) + (1 if fused else 0)   # + the all-gather kernel of the fused all-reduce
     # peak device memory one step adds on top of its inputs and the weights (workspace with the staged logits + outputs)
+    step(0, dev_in)
+    drain()
+    torch.cuda.synchronize()
+    dws[0] = dws[1] = None
     torch.cuda.reset_peak_memory_stats()
     mem0 = torch.cuda.memory_allocated()
     step(0, dev_in)
     drain()
     torch.cuda.synchronize()
     head_peak_extra = int(torch.cuda.max_memory_allocated() - mem0)
+    head.StageTimer.reserve(4 * 8 * cfg["splits"] * (args.steps + 8))   # timing events exist before any timed region starts
+    # the warm-up below is the last thing before the timed region and steps through the same buffer rotation, so the caching
+    # allocator is in its steady state when the clock starts (a cudaMalloc inside the first timed step costs milliseconds)
+    # warm-up in the mode the timed region runs in (stage events recorded by the library); its events are discarded
+    with head.StageTimer() as warm:
+        for i in range(max(3, args.warmup)):
+            res = step(i, dev_in)
+    warm.summary()
+    drain()
+    barrier()
+    launches_per_step = res.launches * (2 if multi_split else 1) + (1 if fused else 0)   # + the all-gather kernel of the fused all-reduce
+
     nv0 = _nvlink_counters(local) if world > 1 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if rank == 0:
         sampler.mark()
     e0.record()
-    with head.StageTimer() as st:   # CUDA events around every launch of the timed region (the live roofline numbers)
+    dbg = [] if os.environ.get("CLEAR_BENCH_DEBUG") else None
+    with head.StageTimer() as st:   # the library records CUDA events between the stages of every step (the live roofline numbers)
         for i in range(args.steps):
+            if dbg is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(); dbg.append((ev, time.perf_counter()))
             res = step(i, dev_in)
         drain()
         e1.record()
         barrier()
     summ = st.summary()
     ms = e0.elapsed_time(e1)
+    if dbg:
+        print("per-step gpu ms:", [round(dbg[i][0].elapsed_time(dbg[i + 1][0]), 2) for i in range(len(dbg) - 1)],
+              "cpu ms:", [round((dbg[i + 1][1] - dbg[i][1]) * 1e3, 2) for i in range(len(dbg) - 1)], file=sys.stderr)
     nv1 = _nvlink_counters(local) if world > 1 else None
     clocks = sampler.stop() if rank == 0 else None
     loss_value = res.loss.item()
@@ -632,7 +647,7 @@ def main():
     gemm_ms = sum(v[1] for k, v in summ.items() if k.startswith("gemm")) / args.steps
     gemm_launches = sum(v[0] for k, v in summ.items() if k.startswith("gemm")) // args.steps
     rowloss_ms = summ.get("rowloss", (0, 0.0))[1] / args.steps
-    staged_all = bool(gemm_launches) and not (compact and args.config in (3, 4, 5))   # compacted invocations run the one-call entry
+    staged_all = bool(gemm_launches)
 
     extras = {}
     if world == 1 and not args.no_extras:
@@ -706,14 +721,14 @@ def main():
                                          if fused else "NCCL all-reduce(avg) of dW per step, overlapped with the next step" + fused_note))
                                        if world > 1 else "none (1 GPU)"},
             "value_one_call": {"value": tokens * args.steps / (ms_one_call * 1e-3), "ms_per_step": ms_one_call / args.steps,
-                               "what": "the same steps through clear_head_loss_fwd_bwd (one C call per invocation, the trainers' path) without per-launch events"},
+                               "what": "the same loop without the library's stage events"},
             "e2e": {"value": tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note,
-                         "kernel": "gemm_bf16_kernel (tcgen05, cta_group::2)" + ("" if staged_all else " — whole step (compacted invocations are not instrumented per launch)"),
-                         "launches_per_step": gemm_launches, "kernel_ms_per_step": kernel_ms,
+                         "kernel": "gemm_bf16_kernel (tcgen05, cta_group::2): student + teacher projection in one launch, dH and dW",
+                         "contraction_stages_per_step": gemm_launches, "kernel_ms_per_step": kernel_ms,
                          "peak_source": peaks["source"] + (", bf16_tflops (burst: the timed region is %.2f s)" % (ms * 1e-3) if short
                                                            else ", bf16_tflops_sustained (timed region %.1f s)" % (ms * 1e-3)),
                          "frac_of_burst_peak": achieved / peaks["tflops_burst"],

@@ -288,7 +288,17 @@ typedef struct ClearHeadArgs {
   /* optional cudaEvent_t: the stream waits on it (cudaStreamWaitEvent) right before the first launch that writes into
    * dweight_peers — the owners have zeroed their slabs — instead of the caller holding the whole invocation back */
   void* dweight_ready_event;
+  /* optional profiling hooks: an array of cudaEvent_t (4 per block of rows, n_stage_events >= 4 * number of blocks or the
+   * surplus blocks go unrecorded) that the library records on the stream before the projection(s) of a block, after them,
+   * after the row pass and after the backward contractions — so that per-kernel times can be measured with CUDA events
+   * INSIDE a timed region that runs this very entry point (bench.py's roofline numbers) */
+  void* const* stage_events;
+  int32_t n_stage_events;
 } ClearHeadArgs;
+/* timing events for ClearHeadArgs::stage_events (cudaEvent_t handles of the library's own CUDA runtime instance) */
+int clear_event_create(void** event);
+int clear_event_elapsed_ms(void* start, void* stop, float* ms_host); /* both events must have completed */
+int clear_event_destroy(void* event);
 int clear_head_loss_workspace_bytes(const ClearHeadArgs* args, size_t* out_bytes);
 int clear_head_loss_fwd_bwd(const ClearHeadArgs* args, void* workspace, size_t workspace_bytes, void* stream);
 

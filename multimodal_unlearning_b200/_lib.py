@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "clear_head_lse_partials_f32", "clear_rows_gather_dev", "clear_rows_scatter_dev", "clear_index_compose",
     "clear_saliency_hist_total", "clear_saliency_select_global_tau", "clear_saliency_select_global_fill",
     "clear_adamw8_block_elems", "clear_masked_adamw_8bit", "clear_head_project_pair",
+    "clear_event_create", "clear_event_elapsed_ms", "clear_event_destroy",
 )
 ABI_VERSION = 3
 
@@ -82,7 +83,8 @@ class HeadArgs(C.Structure):
                 ("reduction", C.c_int32), ("n_seqs", C.c_int32), ("block_rows", C.c_int32), ("dweight_f32", C.c_int32),
                 ("dweight_accumulate", C.c_int32), ("cta_group", C.c_int32),
                 ("row_index", C.c_void_p), ("n_src_rows", C.c_int64), ("compact_ignored", C.c_int32),
-                ("ref_logits_f32", C.c_int32), ("status_flags", C.c_void_p), ("dweight_ready_event", C.c_void_p)]
+                ("ref_logits_f32", C.c_int32), ("status_flags", C.c_void_p), ("dweight_ready_event", C.c_void_p),
+                ("stage_events", C.c_void_p), ("n_stage_events", C.c_int32)]
 
 
 class AdamWArgs(C.Structure):
@@ -162,6 +164,9 @@ def load() -> C.CDLL:
     lib.clear_saliency_select_global_tau.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p]
     lib.clear_saliency_select_global_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                                       C.c_void_p, C.c_void_p]
+    lib.clear_event_create.argtypes = [C.POINTER(C.c_void_p)]
+    lib.clear_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.clear_event_destroy.argtypes = [C.c_void_p]
     lib.clear_adamw8_block_elems.restype = C.c_int32
     lib.clear_masked_adamw_8bit.argtypes = [C.POINTER(AdamW8Args), C.c_void_p]
     lib.clear_head_loss_workspace_bytes.argtypes = [C.POINTER(HeadArgs), C.POINTER(C.c_size_t)]

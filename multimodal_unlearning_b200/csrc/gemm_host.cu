@@ -400,6 +400,26 @@ int clear_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   return 0;
 }
 
+int clear_event_create(void** event) {
+  if (!event) return clear::fail(CLEAR_ERR_NULL, "clear_event_create: NULL");
+  cudaEvent_t e;
+  CLEAR_CUDA_OK(cudaEventCreate(&e));
+  *event = e;
+  return 0;
+}
+
+int clear_event_elapsed_ms(void* start, void* stop, float* ms_host) {
+  if (!start || !stop || !ms_host) return clear::fail(CLEAR_ERR_NULL, "clear_event_elapsed_ms: NULL");
+  CLEAR_CUDA_OK(cudaEventElapsedTime(ms_host, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+  return 0;
+}
+
+int clear_event_destroy(void* event) {
+  if (!event) return 0;
+  CLEAR_CUDA_OK(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+  return 0;
+}
+
 int clear_gemm_bf16(const ClearGemmArgs* g, void* stream) {
   if (!g) return clear::fail(CLEAR_ERR_NULL, "clear_gemm_bf16: args is NULL");
   clear::GemmOperand a{g->a, g->lda, g->a_major};

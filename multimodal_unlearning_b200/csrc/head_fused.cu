@@ -202,6 +202,12 @@ int clear_head_loss_fwd_bwd(const ClearHeadArgs* a, void* workspace, size_t ws_b
   }
 
   const int ref_esz = a->ref_logits_f32 ? 4 : 2;
+  auto stage_event = [&](int64_t b, int k) -> int {   // optional profiling hooks (ClearHeadArgs::stage_events)
+    const int64_t i = 4 * b + k;
+    if (a->stage_events && i < a->n_stage_events && a->stage_events[i])
+      CLEAR_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(a->stage_events[i]), cs));
+    return 0;
+  };
   for (int64_t b = 0; b < p.n_blocks; ++b) {
     const int64_t r0 = b * p.blk, rows = (r0 + p.blk <= a->n_rows ? p.blk : a->n_rows - r0);
     ClearProjectArgs pa = {};
@@ -212,6 +218,7 @@ int clear_head_loss_fwd_bwd(const ClearHeadArgs* a, void* workspace, size_t ws_b
     pa.hidden_ld = hidden_ld; pa.weight_ld = a->weight_ld; pa.logits_ld = p.ld;
     pa.n_rows = rows; pa.hidden_dim = a->hidden_dim; pa.vocab = a->vocab; pa.cta_group = a->cta_group;
     pa.n_rows_dev = count_dev; pa.n_rows_dev_offset = (int32_t)r0;
+    if ((rc = stage_event(b, 0))) return rc;
 
     const void* ref_rows = nullptr;
     int64_t ref_ld = 0;
@@ -238,6 +245,7 @@ int clear_head_loss_fwd_bwd(const ClearHeadArgs* a, void* workspace, size_t ws_b
       if (rc) return rc;
     }
 
+    if ((rc = stage_event(b, 1))) return rc;
     ClearRowLossArgs ra = {};
     ra.logits = z;
     ra.lse_part = part;
@@ -254,6 +262,7 @@ int clear_head_loss_fwd_bwd(const ClearHeadArgs* a, void* workspace, size_t ws_b
     ra.n_rows_dev = count_dev; ra.n_rows_dev_offset = (int32_t)r0;
     ra.status_flags = a->status_flags;
     if ((rc = clear_head_rowloss(&ra, stream))) return rc;
+    if ((rc = stage_event(b, 2))) return rc;
 
     if (p.write_grad) {
       if (b == 0 && a->n_peers > 0 && a->dweight_ready_event)
@@ -276,6 +285,7 @@ int clear_head_loss_fwd_bwd(const ClearHeadArgs* a, void* workspace, size_t ws_b
       ba.n_rows_dev = count_dev; ba.n_rows_dev_offset = (int32_t)r0;
       if ((rc = clear_head_backward(&ba, stream))) return rc;
     }
+    if ((rc = stage_event(b, 3))) return rc;
   }
 
   // ---- results back to the caller's row space ----

@@ -44,13 +44,29 @@ def _stream() -> C.c_void_p:
 
 
 class StageTimer:
-    """Optional per-launch timing with CUDA events on the launching stream (bench.py's live roofline
-    measurement).  `with StageTimer() as t: ...; t.summary()` -> {stage: (launches, total ms)}."""
+    """Optional per-stage timing with CUDA events on the launching stream (bench.py's live roofline measurement).
+    `with StageTimer() as t: ...; t.summary()` -> {stage: (launches, total ms)}.
+
+    By default the timed invocations run the product path — the one-call C entry — and the LIBRARY records the events
+    between its stages (ClearHeadArgs.stage_events): what is timed is what the trainers run.  staged=True drives the stage
+    entry points one by one from Python instead (tests compare the two bit for bit)."""
 
     active: "StageTimer | None" = None
+    _pool: list = []           # idle cudaEvent_t handles (creating one costs ~0.1 ms of host time: they are created once and reused)
 
-    def __init__(self):
-        self.records = []
+    def __init__(self, staged: bool = False):
+        self.staged = staged
+        self.records = []      # (tag, torch event pair) or (tag, raw event pair)
+        self._raw = []
+
+    @classmethod
+    def reserve(cls, n: int) -> None:
+        """Make sure n idle events exist (call before a timed region so that none is created inside it)."""
+        lib = _lib.load()
+        while len(cls._pool) < n:
+            e = C.c_void_p()
+            _lib.check(lib.clear_event_create(C.byref(e)), "clear_event_create")
+            cls._pool.append(e)
 
     def __enter__(self):
         StageTimer.active = self
@@ -59,12 +75,29 @@ class StageTimer:
     def __exit__(self, *exc):
         StageTimer.active = None
 
+    def raw_events(self, n: int):
+        """n cudaEvent_t handles of the library's CUDA runtime, owned by this timer."""
+        StageTimer.reserve(n)
+        out = [StageTimer._pool.pop() for _ in range(n)]
+        self._raw.extend(out)
+        return out
+
     def summary(self) -> dict:
         torch.cuda.synchronize()
+        lib = _lib.load()
         out = {}
         for tag, a, b in self.records:
-            n, ms = out.get(tag, (0, 0.0))
-            out[tag] = (n + 1, ms + a.elapsed_time(b))
+            if isinstance(a, C.c_void_p):
+                ms = C.c_float()
+                _lib.check(lib.clear_event_elapsed_ms(a, b, C.byref(ms)), "clear_event_elapsed_ms")
+                dt = ms.value
+            else:
+                dt = a.elapsed_time(b)
+            n, tot = out.get(tag, (0, 0.0))
+            out[tag] = (n + 1, tot + dt)
+        StageTimer._pool.extend(self._raw)   # back to the pool (never destroyed: a few KB for the life of the process)
+        self._raw = []
+        self.records = []
         return out
 
 
@@ -364,8 +397,9 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
     launches = 0
 
     host_scale, grad_scale, per_valid = _normalisation(kind, reduction, n, v, beta, n_seqs)
-    pipelined = overlap and n_blocks >= 2 and StageTimer.active is None and not mapped
-    one_call = not pipelined and (StageTimer.active is None or mapped)   # row maps live in the one-call entry only
+    timer = StageTimer.active
+    pipelined = overlap and n_blocks >= 2 and timer is None and not mapped
+    one_call = not pipelined and (timer is None or not timer.staged or mapped)   # row maps live in the one-call entry only
     inv_count = None
     if per_valid and not one_call:
         inv_count = torch.empty(1, dtype=torch.float32, device=dev)
@@ -456,7 +490,21 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
         need = C.c_size_t()
         _lib.check(lib.clear_head_loss_workspace_bytes(C.byref(a), C.byref(need)), "clear_head_loss_workspace_bytes")
         ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=dev)
+        if timer is not None:   # the library records events between its stages: 4 per block of rows
+            evs = timer.raw_events(4 * n_blocks)
+            table = (C.c_void_p * len(evs))(*[e.value for e in evs])
+            a.stage_events = C.cast(table, C.c_void_p)
+            a.n_stage_events = len(evs)
         _lib.check(lib.clear_head_loss_fwd_bwd(C.byref(a), ws.data_ptr(), need.value, _stream()), "clear_head_loss_fwd_bwd")
+        if timer is not None:
+            proj_tag = "gemm_project_pair" if (needs_ref and ref_logits is None) else ("gemm_project+ref_lse" if needs_ref else "gemm_project")
+            for b in range(n_blocks):
+                e = evs[4 * b: 4 * b + 4]
+                timer.records.append((proj_tag, e[0], e[1]))
+                timer.records.append(("rowloss", e[1], e[2]))
+                if write_grad:
+                    tag = "gemm_backward" if (need_dhidden and need_dweight) else ("gemm_dhidden" if need_dhidden else "gemm_dweight")
+                    timer.records.append((tag, e[2], e[3]))
         if need_dweight and peers is None and dweight_accum is None and dweight.dtype != torch.bfloat16:
             dweight = dweight.to(torch.bfloat16)
         return HeadResult(loss, seq_loss, dhidden, dweight if peers is None else None, loss_rows, launches)

@@ -685,10 +685,16 @@ def test_one_call_entry_equals_the_staged_entry_points(kind):
     kw = dict(labels=y.to(dev), ref_hidden=rh.to(dev), ref_weight=rw.to(dev), beta=0.7 if kind == HO.KIND_NPO else 1.0, coef=-0.7,
               block_rows=128)
     one = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), kind, **kw)
-    with head.StageTimer() as st:
+    with head.StageTimer(staged=True) as st:
         staged = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), kind, **kw)
     summ = st.summary()
     assert any(k.startswith("gemm") for k in summ) and "rowloss" in summ
+    # default timer: the one-call entry itself, events recorded by the library between its stages (3 blocks of 128 rows)
+    with head.StageTimer() as st2:
+        timed = head.head_loss_fwd_bwd(hid.to(dev), w.to(dev), kind, **kw)
+    summ2 = st2.summary()
+    assert summ2["rowloss"][0] == 3 and summ2["gemm_backward"][0] == 3 and all(v[1] > 0 for v in summ2.values())
+    assert torch.equal(timed.loss, one.loss) and torch.equal(timed.dweight, one.dweight)
     assert torch.equal(one.loss, staged.loss) and torch.equal(one.loss_rows, staged.loss_rows)
     assert torch.equal(one.dhidden, staged.dhidden) and torch.equal(one.dweight, staged.dweight)
     assert one.launches == staged.launches

@@ -17,7 +17,7 @@ ref = (hid.float() + 0.05 * torch.randn(N, H, generator=g, device=dev)).to(torch
 w = (0.02 * torch.randn(V, H, generator=g, device=dev)).to(torch.bfloat16)
 y = torch.randint(0, V, (N,), generator=g, device=dev)
 sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "8192,4096,2048,1024".split(","))]
-rounds, steps = 7, 8
+rounds, steps = 15, 6
 
 
 OVERLAP = len(sys.argv) > 2 and sys.argv[2] == "overlap"
