@@ -7,6 +7,15 @@ O, P = ROOT / "gpurun_out", ROOT / "profiles"
 pre = sys.argv[1] if len(sys.argv) > 1 else "r02f_"
 
 
+def plain_ms(d):
+    """ms per step of the loop without stage events (the headline loop since the final build; `value_one_call` before)."""
+    return d["ms_per_step"] if "value_with_stage_events" in d else d["value_one_call"]["ms_per_step"]
+
+
+def staged_ms(d):
+    return d["value_with_stage_events"]["ms_per_step"] if "value_with_stage_events" in d else d["ms_per_step"]
+
+
 def last_json(path):
     return json.loads(Path(path).read_text().strip().splitlines()[-1])
 
@@ -24,13 +33,13 @@ md = ["# Round 2 — every BASELINE.json config on one B200 (loss head only, dev
       "dH / dW; for compacted CE terms in (1): the flops of the rows that carry a label); peaks from MEASURED_PEAKS.json",
       f"(bf16 {b['roofline']['peak']:.1f} TFLOP/s burst).\n",
       "## (1) `bench.py --config K`\n",
-      "| config | loss_type | row compaction | ms/step | tokens/s | same loop without stage events ms/step | e2e tokens/s | contraction TFLOP/s | frac of burst peak | stages ms/step |", "|---|---|---|---|---|---|---|---|---|---|"]
+      "| config | loss_type | row compaction | ms/step | tokens/s | same loop with stage events ms/step | e2e tokens/s | contraction TFLOP/s | frac of burst peak | stages ms/step |", "|---|---|---|---|---|---|---|---|---|---|"]
 rows = [(2, b)] + [(c, last_json(O / f"{pre}cfg{c}.json")) for c in (3, 4, 5) if (O / f"{pre}cfg{c}.json").exists()]
 for c, d in rows:
     r = d["roofline"]
     st = ", ".join(f"{k} {v[1]:.3f}" for k, v in r["stages_ms_per_step"].items())
-    md.append(f"| cfg {c} = {d['config']['baseline_config']} | {d['config']['loss_type']} | {d['config']['row_compaction']} | {d['ms_per_step']:.3f} | {d['value']:.0f} | "
-              f"{d['value_one_call']['ms_per_step']:.3f} | {d['e2e']['value']:.0f} | {r['achieved']:.0f} | {r['frac_of_burst_peak']:.3f} | {st} |")
+    md.append(f"| cfg {c} = {d['config']['baseline_config']} | {d['config']['loss_type']} | {d['config']['row_compaction']} | {plain_ms(d):.3f} | {d['config']['rows_per_gpu'] / plain_ms(d) * 1e3:.0f} | "
+              f"{staged_ms(d):.3f} | {d['e2e']['value']:.0f} | {r['achieved']:.0f} | {r['frac_of_burst_peak']:.3f} | {st} |")
 md += ["", "cfg 4's labels leave 5-15 rows per sequence: after compaction the step is a handful of small launches (0.3-0.4 ms; the 501-K-block",
        "tiles of dH over one row tile bound it), its 'fraction of peak' says nothing about the kernels.  cfg 3 compacts its CE split (65 % of",
        "the forget rows ignored) and evaluates every row of its KL split, as the reference does.\n",
@@ -44,8 +53,8 @@ g = b.get("gpu_eager_baseline")
 if g:
     md += ["", "## GPU-side eager baseline (the reference's chain on the same B200)\n",
            f"`gpu_eager_baseline`: {g['kind']}.  **{g['ms_per_step']:.2f} ms per step ({g['value']:.0f} tokens/s), {g['peak_extra_bytes'] / 1e9:.2f} GB of extra",
-           f"device memory** against {b['value_one_call']['ms_per_step']:.2f} ms and {b['config'].get('peak_extra_bytes_per_step', 0) / 1e9:.2f} GB here: "
-           f"**{g['ms_per_step'] / b['value_one_call']['ms_per_step']:.2f}x** faster at {g['peak_extra_bytes'] / max(b['config'].get('peak_extra_bytes_per_step', 1), 1):.1f}x less memory "
+           f"device memory** against {plain_ms(b):.2f} ms and {b['config'].get('peak_extra_bytes_per_step', 0) / 1e9:.2f} GB here: "
+           f"**{g['ms_per_step'] / plain_ms(b):.2f}x** faster at {g['peak_extra_bytes'] / max(b['config'].get('peak_extra_bytes_per_step', 1), 1):.1f}x less memory "
            f"(same loss: {g['loss']:.6f} vs {b['config']['loss']:.6f}).  CPU arm (oracle port of the reference, {ref['cpu_baseline']['cores']} host threads, fp32, "
            f"2048-row sample): {ref['value']:.0f} tokens/s."]
 (P / "r02_configs.md").write_text("\n".join(md) + "\n")
