@@ -232,7 +232,13 @@ def sharded_masks(state: SaliencyState, thresholds: Sequence[float] = REFERENCE_
     scope="global" (upstream SalUn's global rank): rank r owns a contiguous 1/R slice of the flat buffer (whole mask
     chunks); it histograms its slice, the 32768-bin totals are all-reduced over NCCL (256 KB), every rank derives the same
     threshold key and tie budget, the budget is split over ranks by an exclusive prefix in slice (= flat index) order
-    (`distributed.tie_budget_for_rank`), each rank writes the mask of its slice, one all-gather per threshold."""
+    (`distributed.tie_budget_for_rank`), each rank writes the mask of its slice, one all-gather per threshold.
+
+    Measured on 2 x B200 at 6.74 B parameters (profiles/r02_sharded_masks.md): both scopes reproduce the one-GPU masks bit for
+    bit, and neither beats a rank that simply computes every mask itself (29 ms for ten thresholds: the masks come out of HBM
+    faster than NVLink can deliver them) — under DDP call `state.select(...)` / `mask_flat` on every rank after the
+    accumulator's all-reduce; this function is for consumers that shard the parameters (and for the north-star's histogram
+    reduction: only the 256 KB histogram and the tie budgets cross ranks to fix the threshold)."""
     import torch.distributed as dist
 
     from . import distributed as D
