@@ -7,11 +7,19 @@
 //     one thread, fp32 accumulators in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile
 //     i overlaps the main loop of tile i+1;
 //   * work items (output tile x K split) are CLAIMED, not assigned: the TMA thread of each CTA pair's leader takes the
-//     next item from a global counter one item ahead of its own pipeline and publishes it through a 4-slot shared-
-//     memory ring (mbarrier full/empty, mirrored into the peer CTA over DSMEM) to the MMA thread and the epilogue
-//     warps.  A CTA pair that the hardware launches late — its SMs were held by an NCCL kernel of the overlapped
-//     gradient all-reduce — simply finds less work left, instead of holding its statically assigned tiles hostage
+//     next item from a global counter one item ahead of its own pipeline, DECODES it (problem, tile coordinates, K-block
+//     range: the integer divisions run once per item, in the thread with the most slack) and publishes the decoded item
+//     through an 8-slot shared-memory ring to the MMA thread, the second TMA thread, the epilogue warps and the peer CTA —
+//     one st.async per CTA (16 bytes + complete_tx on that CTA's mbarrier: no fence anywhere), a few K blocks into the
+//     current item, so every reader knows its next item a whole tile early and the MMA-issuing thread's tile boundary
+//     is a 16-byte shared load.  Consumers hand slots and TMEM stages back with fence-free remote arrives.
+//     A CTA pair that the hardware launches late — its SMs were held by an NCCL kernel of the overlapped gradient
+//     all-reduce — simply finds less work left, instead of holding its statically assigned tiles hostage
 //     (measured at 2 GPUs with a static schedule: +0.5 ms per 6.5 ms step, +1.9 ms with NCCL limited to 4 CTAs);
+//   * operand A and operand B are loaded by TWO TMA threads (warps 0 and 3): with MN-major operands a K block takes four
+//     bulk-tensor instructions per CTA, and one thread issuing all of them was busy 80 % of the K-block time;
+//     ncu, N = 8192 / H = 4096 / V = 32064, before -> after (fence-free hand-backs, decoded ring, second TMA thread):
+//     tensor pipe active 91.7 -> 99.3 % (projection pair), 98.1 -> 99.1 % (dH), 94.3 -> 98.4 % (dW);
 //   * epilogue warps read TMEM with tcgen05.ld, optionally fold an online log-sum-exp over the
 //     (bf16-rounded) logits of their rows, convert, stage through swizzled smem and TMA-store
 //     (or TMA reduce-add for fp32 accumulation into an existing dW).
@@ -89,10 +97,10 @@ struct GemmShape {
   static constexpr int STAGES = (kCtaGroup == 2) ? 6 : 4;
   static constexpr int EPI_WARP_BYTES = 2 * 4096;   // two 32-row x 128 B staging buffers per warp
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-  static constexpr int SCHED_SLOTS = 4;             // ring of claimed work items shared by every role of the CTA pair
-  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * SCHED_SLOTS) * 8 + 16 + SCHED_SLOTS * 4;
+  static constexpr int SCHED_SLOTS = 8;             // ring of claimed, decoded work items shared by every role of the CTA pair
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * SCHED_SLOTS) * 8 + 16 + SCHED_SLOTS * 16;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-  static constexpr int THREADS = 256;               // warps 0..3: TMA / MMA / TMEM-alloc / idle; 4..7 epilogue
+  static constexpr int THREADS = 256;               // warps 0..3: TMA (operand A, scheduler) / MMA / TMEM-alloc / TMA (operand B); 4..7 epilogue
   static constexpr int TMEM_COLS = 512;             // 2 accumulator stages x 256 fp32 columns
 };
 
@@ -121,6 +129,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_major, int
          | (uint32_t(m >> 4) << 24);
 }
 
+constexpr int kHandOnAfter = 8;   // K blocks of an item after which the leader's TMA thread decodes and publishes the next one
+
 template <int kCtaGroup, int kMajorA, int kMajorB, int kEpi>
 __global__ void __launch_bounds__(GemmShape<kCtaGroup>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -142,7 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_slot = tempty_bar + 16;
   const uint32_t sfull_bar = tmem_slot + 16;                       // [SCHED_SLOTS] item published (one per CTA)
   const uint32_t sempty_bar = sfull_bar + S::SCHED_SLOTS * 8;      // [SCHED_SLOTS] every reader is done (leader CTA's copy is used)
-  const uint32_t sched_item = sempty_bar + S::SCHED_SLOTS * 8;     // [SCHED_SLOTS] uint32 work item
+  const uint32_t sched_item = sempty_bar + S::SCHED_SLOTS * 8;     // [SCHED_SLOTS] uint4: work item, M tile, N tile, K-block range | problem
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -174,8 +184,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < S::SCHED_SLOTS; ++i) {
       ptx::mbar_init(sfull_bar + i * 8, 1);
-      // readers of a slot: the leader's MMA thread + 4 epilogue warps; in the peer CTA its TMA thread + 4 epilogue warps
-      ptx::mbar_init(sempty_bar + i * 8, 5 * kCtaGroup);
+      // readers of a slot: operand B's TMA thread + 4 epilogue warps + (leader CTA: the MMA thread; peer CTA: operand A's TMA thread)
+      ptx::mbar_init(sempty_bar + i * 8, 6 * kCtaGroup);
     }
     ptx::fence_barrier_init();
   }
@@ -228,12 +238,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nkb1 = (K1 + S::BK - 1) / S::BK;
 
   // Work item -> problem, output tile, K-block range.  Chunks of `raster_group` tiles along the fast dimension, each swept
-  // across the slow one.
+  // across the slow one.  Only the leader's TMA thread decodes; everybody else reads the result from the ring.
   struct Item {
-    int second, mt, nt, kb0, kb1;
+    int w, second, mt, nt, kb0, kb1;
   };
   auto decode = [&](int w) {
     Item it;
+    it.w = w;
     it.second = (two && w >= base1) ? 1 : 0;
     const GemmProblem& q = p.q[it.second];
     const int m_tiles = it.second ? mt1 : mt0;
@@ -249,74 +260,83 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     const int fast_tiles = q.raster_m_fast ? m_tiles : q.n_tiles;
     const int slow_tiles = q.raster_m_fast ? q.n_tiles : m_tiles;
-    const int per_chunk = q.raster_group * slow_tiles;
+    const int per_chunk = max(q.raster_group * slow_tiles, 1);
     const int c = t / per_chunk;
     const int r = t - c * per_chunk;
-    const int g = min(q.raster_group, fast_tiles - c * q.raster_group);
+    const int g = max(min(q.raster_group, fast_tiles - c * q.raster_group), 1);
     const int slow = r / g;
     const int fast = c * q.raster_group + (r - slow * g);
     it.mt = q.raster_m_fast ? fast : slow;
     it.nt = q.raster_m_fast ? slow : fast;
     return it;
   };
+  // ring slot <-> Item: {w, mt, nt, kb0 | kb1 << 15 | second << 30}  (K blocks < 32768: K < 2 M)
+  auto unpack_item = [&](const uint4 v) {
+    Item it;
+    it.w = (int)v.x; it.mt = (int)v.y; it.nt = (int)v.z;
+    it.kb0 = (int)(v.w & 0x7fffu); it.kb1 = (int)((v.w >> 15) & 0x7fffu); it.second = (int)(v.w >> 30);
+    return it;
+  };
 
-  // Reader side of the scheduler ring.  Every reader consumes every slot in order, the end-of-work item (>= num_tiles)
-  // included.  Called by one thread; the epilogue warps broadcast the result with a shuffle.
-  auto sched_read = [&](uint32_t& slot, uint32_t& sphase) -> int {
-    ptx::mbar_wait<kCtaGroup == 2>(sfull_bar + slot * 8, sphase);
-    const int w = (int)ptx::ld_shared_u32(sched_item + slot * 4);
-    if constexpr (kCtaGroup == 2) ptx::mbar_arrive_cluster(sempty_bar + slot * 8, 0);
+  // Reader side of the scheduler ring.  Every reader consumes every slot in order, the end-of-work item (w >= num_tiles)
+  // included.  Called by one thread; the epilogue warps broadcast the result with shuffles.
+  auto sched_read = [&](uint32_t& slot, uint32_t& sphase) -> Item {
+    ptx::mbar_wait(sfull_bar + slot * 8, sphase);
+    const uint4 v = ptx::ld_shared_v4(sched_item + slot * 16);
+    if constexpr (kCtaGroup == 2) ptx::mbar_arrive_cluster_noflush(sempty_bar + slot * 8, 0);   // a read hand-back: no fence
     else                          ptx::mbar_arrive(sempty_bar + slot * 8);
     if (++slot == S::SCHED_SLOTS) { slot = 0; sphase ^= 1u; }
-    return w;
+    return unpack_item(v);
   };
 
   if (warp == 0) {
     // ===================================== TMA producer ==========================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
-      // Leader: claim an item, publish it to both CTAs of the pair.  The claim for the NEXT item is issued before this
-      // item's loads, so the round trip to L2 hides behind the K loop.
-      auto publish = [&](uint32_t item) {
-        ptx::mbar_wait<kCtaGroup == 2>(sempty_bar + slot * 8, sphase ^ 1u);
+      // Leader: claim an item, decode it, hand it to both CTAs of the pair.
+      auto publish = [&](const Item& it) {
+        ptx::mbar_wait(sempty_bar + slot * 8, sphase ^ 1u);
+        const uint32_t packed = (uint32_t)it.kb0 | ((uint32_t)it.kb1 << 15) | ((uint32_t)it.second << 30);
 #pragma unroll
         for (uint32_t c = 0; c < (uint32_t)kCtaGroup; ++c) {
           if constexpr (kCtaGroup == 2) {
-            ptx::st_shared_cluster_u32(sched_item + slot * 4, c, item);
-            ptx::mbar_arrive_cluster(sfull_bar + slot * 8, c);
+            ptx::mbar_arrive_expect_tx_cluster(sfull_bar + slot * 8, c, 16);
+            ptx::st_async_v4(sched_item + slot * 16, sfull_bar + slot * 8, c, (uint32_t)it.w, (uint32_t)it.mt, (uint32_t)it.nt, packed);
           } else {
-            ptx::st_shared_u32(sched_item + slot * 4, item);
+            ptx::st_shared_v4(sched_item + slot * 16, (uint32_t)it.w, (uint32_t)it.mt, (uint32_t)it.nt, packed);
             ptx::mbar_arrive(sfull_bar + slot * 8);
           }
         }
         if (++slot == S::SCHED_SLOTS) { slot = 0; sphase ^= 1u; }
       };
       const bool leader = (cta_rank == 0);
-      int w = 0;
+      Item it;
       if (leader) {
-        w = (int)atomicAdd(p.work_counter, 1u);
-        publish((uint32_t)w);
+        it = decode((int)atomicAdd(p.work_counter, 1u));
+        publish(it);
       } else {
-        w = sched_read(slot, sphase);
+        it = sched_read(slot, sphase);
       }
-      while (w < num_tiles) {
+      while (it.w < num_tiles) {
+        // The claim for the NEXT item is issued before this item's loads and handed on kHandOnAfter K blocks in, when the
+        // counter's reply has long arrived and the pipeline is full again: the round trip to L2 and the decoding hide behind
+        // the K loop, and every reader has its next item long before it reaches its own tile boundary.  (Measured, ncu, N =
+        // 8192: handing on after 2 / 8 K blocks: projection pair 98.9 / 99.3 % tensor-pipe active.)
         unsigned int next_claim = 0;
         if (leader) next_claim = atomicAdd(p.work_counter, 1u);
-        const Item it = decode(w);
         const CUtensorMap* mA = it.second ? &tmA1 : &tmA;
-        const CUtensorMap* mB = it.second ? &tmB1 : &tmB;
         const bool a_mn = (kMajorA == kMajorRuntime) ? (p.q[it.second].a_major == kMajorMN) : (kMajorA == kMajorMN);
         const int m0 = (it.mt * kCtaGroup + (int)cta_rank) * S::BM;
-        const int n0 = it.nt * S::BN + (int)cta_rank * S::B_ROWS;
-        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        // Operand A of one K block (operand B comes from the second TMA thread, warp 3: with MN-major operands a K block
+        // takes four bulk-tensor instructions per CTA, and one thread issuing all of them ran at 80 % of the K-block time —
+        // any hiccup starved the tensor pipe).  K-major: one box [rows][64 k].  MN-major: one box [64 k][64 mn] per
+        // 64-element MN chunk, chunks 8 KB apart (= the descriptor's LBO).
+        auto load_a = [&](int kb) {
           ptx::mbar_wait(empty_bar + stage * 8, phase ^ 1u);
           const uint32_t fb = full_bar + stage * 8;
           if (cta_rank == 0) ptx::mbar_arrive_expect_tx(fb, S::STAGE_BYTES * kCtaGroup);
           const uint32_t a_dst = smem_base + stage * S::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + S::A_BYTES;
           const int k0 = kb * S::BK;
-          // K-major: one box [rows][64 k].  MN-major: one box [64 k][64 mn] per 64-element MN chunk,
-          // chunks 8 KB apart (= the descriptor's LBO).
           if (!a_mn) {
             ptx::tma_load_2d<kCtaGroup>(a_dst, mA, fb, k0, m0);
           } else {
@@ -324,20 +344,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int c = 0; c < S::BM / 64; ++c)
               ptx::tma_load_2d<kCtaGroup>(a_dst + c * (S::BK * 128), mA, fb, m0 + c * 64, k0);
           }
-          if constexpr (kMajorB == kMajorK) {
-            ptx::tma_load_2d<kCtaGroup>(b_dst, mB, fb, k0, n0);
-          } else {
-#pragma unroll
-            for (int c = 0; c < S::B_ROWS / 64; ++c)
-              ptx::tma_load_2d<kCtaGroup>(b_dst + c * (S::BK * 128), mB, fb, n0 + c * 64, k0);
-          }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1u; }
-        }
+        };
+        const int kb_hand_on = min(it.kb0 + kHandOnAfter, it.kb1);
+        for (int kb = it.kb0; kb < kb_hand_on; ++kb) load_a(kb);
         if (leader) {
-          w = (int)next_claim;
-          publish(next_claim);
+          const Item nxt = decode((int)next_claim);
+          publish(nxt);
+          for (int kb = kb_hand_on; kb < it.kb1; ++kb) load_a(kb);
+          it = nxt;
         } else {
-          w = sched_read(slot, sphase);
+          for (int kb = kb_hand_on; kb < it.kb1; ++kb) load_a(kb);
+          it = sched_read(slot, sphase);
         }
       }
     }
@@ -348,8 +366,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t b_adv = (kMajorB == kMajorK) ? (S::UMMA_K * 2) : (S::UMMA_K * 128);
       constexpr uint32_t b_lbo = (kMajorB == kMajorK) ? 16u : (S::BK * 128);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
-      for (int w = sched_read(slot, sphase); w < num_tiles; w = sched_read(slot, sphase)) {
-        const Item it = decode(w);
+      for (Item it = sched_read(slot, sphase); it.w < num_tiles; it = sched_read(slot, sphase)) {
         const bool a_mn = (kMajorA == kMajorRuntime) ? (p.q[it.second].a_major == kMajorMN) : (kMajorA == kMajorMN);
         const uint32_t idesc = make_idesc(S::BM * kCtaGroup, S::BN, a_mn ? 1 : 0, kMajorB);
         const uint32_t a_adv = a_mn ? (S::UMMA_K * 128) : (S::UMMA_K * 2);
@@ -377,6 +394,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+  } else if (warp == 3) {
+    // ===================================== TMA producer, operand B =================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
+      for (Item it = sched_read(slot, sphase); it.w < num_tiles; it = sched_read(slot, sphase)) {
+        const CUtensorMap* mB = it.second ? &tmB1 : &tmB;
+        const int n0 = it.nt * S::BN + (int)cta_rank * S::B_ROWS;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          // the stage's barrier is armed by operand A's thread of the leader CTA (expect_tx covers both operands of both
+          // CTAs); bytes that land before that leave the transaction count negative for a moment, which mbarriers allow
+          ptx::mbar_wait(empty_bar + stage * 8, phase ^ 1u);
+          const uint32_t fb = full_bar + stage * 8;
+          const uint32_t b_dst = smem_base + stage * S::STAGE_BYTES + S::A_BYTES;
+          const int k0 = kb * S::BK;
+          if constexpr (kMajorB == kMajorK) {
+            ptx::tma_load_2d<kCtaGroup>(b_dst, mB, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < S::B_ROWS / 64; ++c)
+              ptx::tma_load_2d<kCtaGroup>(b_dst + c * (S::BK * 128), mB, fb, n0 + c * 64, k0);
+          }
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================================== epilogue ==============================================
     const uint32_t q4 = warp & 3u;  // TMEM lane quadrant this warp may read
@@ -384,11 +426,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t sw = (lane & 7u);
     uint32_t nstores = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
     while (true) {
-      int w = 0;
-      if (lane == 0) w = sched_read(slot, sphase);
-      w = __shfl_sync(0xffffffffu, w, 0);
-      if (w >= num_tiles) break;
-      const Item it = decode(w);
+      Item it = {};
+      if (lane == 0) it = sched_read(slot, sphase);
+      it.w = __shfl_sync(0xffffffffu, it.w, 0);
+      if (it.w >= num_tiles) break;
+      it.mt = __shfl_sync(0xffffffffu, it.mt, 0);
+      it.nt = __shfl_sync(0xffffffffu, it.nt, 0);
+      it.kb0 = __shfl_sync(0xffffffffu, it.kb0, 0);
+      it.kb1 = __shfl_sync(0xffffffffu, it.kb1, 0);
+      it.second = __shfl_sync(0xffffffffu, it.second, 0);
       const GemmProblem& q = p.q[it.second];
       const int dynM = it.second ? M1 : M0;
       const bool no_k = it.kb1 <= it.kb0;   // no MMA ran: the accumulator is not defined, the tile is all zeros
@@ -496,7 +542,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kCtaGroup == 2) ptx::mbar_arrive_cluster(tempty_bar + acc * 8, 0);
+        if constexpr (kCtaGroup == 2) ptx::mbar_arrive_cluster_noflush(tempty_bar + acc * 8, 0);
         else                          ptx::mbar_arrive(tempty_bar + acc * 8);
       }
       acc ^= 1u;

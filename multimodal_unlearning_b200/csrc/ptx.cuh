@@ -63,6 +63,22 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       : "memory");
 }
 
+// The same for "I am done READING" hand-backs (a consumer returning a scheduler slot or a TMEM accumulator stage to the
+// leader CTA): nothing this thread wrote has to become visible, so the arrive carries the default semantics instead of
+// .release.cluster — the latter compiles to MEMBAR.ALL.CTA (.GPU after a global store) + ERRBAR in front of the
+// SYNCS.ARRIVE, which held the single MMA-issuing thread ~1.7 us per output tile (ncu source page, round 2: 6.5 % of its
+// samples) while the tensor pipe drained.  The tcgen05 side is ordered by tcgen05.fence::before_thread_sync / after_thread_sync.
+__device__ __forceinline__ void mbar_arrive_cluster_noflush(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 raddr;\n"
+      "mapa.shared::cluster.u32 raddr, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [raddr];\n"
+      "}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -103,6 +119,39 @@ __device__ __forceinline__ void st_shared_cluster_u32(uint32_t addr, uint32_t ct
       "}" ::"r"(addr),
       "r"(cta), "r"(value)
       : "memory");
+}
+
+// Hand 16 bytes to CTA `cta` of the cluster and signal its mbarrier in ONE asynchronous operation: the store carries
+// complete_tx on the destination CTA's barrier, so data and signal are ordered by the hardware and the sender needs no fence
+// (st.shared::cluster + mbarrier.arrive.release.cluster costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per destination).  The
+// barrier's phase is armed by mbar_arrive_expect_tx_cluster (16 bytes); the receiver waits with a plain try_wait, as for TMA.
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t bar, uint32_t cta, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 raddr, rbar;\n"
+      "mapa.shared::cluster.u32 raddr, %0, %2;\n"
+      "mapa.shared::cluster.u32 rbar, %1, %2;\n"
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [raddr], {%3, %4, %5, %6}, [rbar];\n"
+      "}" ::"r"(addr),
+      "r"(bar), "r"(cta), "r"(a), "r"(b), "r"(c), "r"(d)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar, uint32_t cta, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 rbar;\n"
+      "mapa.shared::cluster.u32 rbar, %0, %1;\n"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [rbar], %2;\n"
+      "}" ::"r"(bar),
+      "r"(cta), "r"(bytes)
+      : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t value) {
