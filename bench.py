@@ -563,6 +563,9 @@ def main():
     drain()
     barrier()
     launches_per_step = res.launches * (2 if multi_split else 1) + (1 if fused else 0)   # + the all-gather kernel of the fused all-reduce
+    # a result kept alive across the timed loop is a FOURTH set of buffers beside the two in `dws` and the one being computed: the
+    # caching allocator, warmed up on three, answers the second timed step with a cudaMalloc of a gigabyte (1-40 ms, seen on cfg 5)
+    del res
 
     def timed_loop(tag):
         """K steps between two CUDA events on the launching stream, barrier + synchronize on both sides."""
@@ -583,13 +586,13 @@ def main():
         if dbg:
             print(tag, "per-step gpu ms:", [round(dbg[i][0].elapsed_time(dbg[i + 1][0]), 2) for i in range(len(dbg) - 1)],
                   "cpu ms:", [round((dbg[i + 1][1] - dbg[i][1]) * 1e3, 2) for i in range(len(dbg) - 1)], file=sys.stderr)
-        return t0.elapsed_time(t1), r
+        return t0.elapsed_time(t1), r.loss   # the scalar only: a HeadResult kept alive would be one more set of buffers
 
     # ---- the timed region: K steps through the one-call C entry, exactly what the trainers run ------------------------
     nv0 = _nvlink_counters(local) if world > 1 else None
     if rank == 0:
         sampler.mark()
-    ms, res = timed_loop("headline")
+    ms, _ = timed_loop("headline")
     nv1 = _nvlink_counters(local) if world > 1 else None
 
     # ---- the same K steps again with the library recording CUDA events between its stages (the live roofline numbers) --
@@ -601,10 +604,10 @@ def main():
     warm.summary()
     drain()
     with head.StageTimer() as st:
-        ms_staged, res = timed_loop("stage events")
+        ms_staged, loss_t = timed_loop("stage events")
     summ = st.summary()
     clocks = sampler.stop() if rank == 0 else None
-    loss_value = res.loss.item()
+    loss_value = loss_t.item()
 
     # ---- end to end: host buffers in, loss out, copies inside the timed region -------------------
     names = [k for k in dev_in]

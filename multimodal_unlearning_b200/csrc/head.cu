@@ -811,10 +811,12 @@ extern "C" {
 int clear_head_vtiles(int vocab) { return (vocab + 255) / 256; }
 
 // diagnostic switch CLEAR_GEMM_GROUP=0: every contraction is its own launch (the round-1 schedule); read once
-static bool group_launches() {
-  static const bool on = [] { const char* e = getenv("CLEAR_GEMM_GROUP"); return e ? atoi(e) != 0 : true; }();
-  return on;
+static int group_level() {
+  static const int level = [] { const char* e = getenv("CLEAR_GEMM_GROUP"); return e ? atoi(e) : 2; }();
+  return level;   // 0: never; 1: projection pair always, dH + dW only where dH alone starves its last wave (the round-2 default
+                  // before the fence-free scheduler ring); 2 (default): dH + dW always
 }
+static bool group_launches() { return group_level() != 0; }
 
 static int project_desc(const ClearProjectArgs* a, GemmDesc* g) {
   if (!a) return fail(CLEAR_ERR_NULL, "clear_head_project: args is NULL");
@@ -1068,14 +1070,16 @@ int clear_head_backward(const ClearBackwardArgs* a, void* stream_) {
   if (a->n_peers < 0 || a->n_peers > 8) return fail(CLEAR_ERR_SHAPE, "clear_head_backward: 0 <= n_peers <= 8");
   if (a->n_peers > 0 && a->dweight_f32) return fail(CLEAR_ERR_KIND, "clear_head_backward: the peer reduce-scatter accumulates in bf16");
   const bool want_dw = a->dweight || a->n_peers > 0;
-  // Both gradients, both bf16: ONE launch when dH on its own would leave its last wave of SM pairs mostly idle (few row
-  // tiles: small staging blocks, compacted rows) — the 501-K-block tiles of dH = dZ W come first, the shorter tiles of
-  // dW = dZ^T H fill the SMs that finish early, so dH needs no split-K scratch (no zeroing, no conversion pass) and the two
-  // share one pipeline ramp and one tail.  With full waves (8192 rows: 6.92 of 7) two launches measured 1.5 % faster
-  // (tools/r02_group_ab.sh, same box, alternating processes), so that case keeps them.
+  // Both gradients, both bf16: ONE launch — the 501-K-block tiles of dH = dZ W come first, the shorter tiles of dW = dZ^T H
+  // fill the SM pairs that finish early, so the two share one pipeline ramp and one tail (dH alone: 6.92 of 7 waves, dW alone:
+  // 27.2 of 28) and dH needs no split-K scratch (no zeroing, no conversion pass) when its row count is small (small staging
+  // blocks, compacted rows).  At full waves (8192 rows) one launch measured 1.5 % SLOWER than two while every tile boundary
+  // cost the MMA thread a fence (round 2, first half); with the fence-free scheduler ring it measures 1.3 % of the NPO step
+  // faster (4 of 4 alternating pairs of processes on one box, tools/r02_group_ab2.sh), so it is the default everywhere.
+  // CLEAR_GEMM_GROUP=1 restores the old rule, 0 separates everything.
   const bool dh_starved = a->n_rows_dev != nullptr ||
                           gemm_pick_k_splits(a->cta_group, (int)a->n_rows, a->hidden_dim, a->vocab) > 1;
-  if (a->dhidden && want_dw && !a->dweight_f32 && dh_starved && group_launches()) {
+  if (a->dhidden && want_dw && !a->dweight_f32 && (dh_starved || group_level() >= 2) && group_launches()) {
     if (!a->weight || !a->hidden) return fail(CLEAR_ERR_NULL, "clear_head_backward: weight and hidden are required");
     GemmDesc gh, gw;
     gh.a = GemmOperand{a->dlogits, a->dlogits_ld, kMajorK};
