@@ -444,9 +444,8 @@ def head_loss_fwd_bwd(hidden: torch.Tensor, weight: torch.Tensor, kind: int, *, 
 
     paired_proj = needs_ref and ref_logits is None                      # student + teacher projection: one launch
     dw_f32 = need_dweight and (dweight_accum is not None or (peers is None and dweight is not None and dweight.dtype == torch.float32))
-    # dH + dW: one launch when both are bf16 and dH alone would starve its last wave (small blocks, compacted rows); the
-    # count below assumes the starved case for blocks under 8192 rows and compaction — it is the library that decides
-    paired_bwd = need_dhidden and need_dweight and not dw_f32 and (compact_ignored or blk < 8192)
+    # dH + dW: one launch whenever both are bf16 (csrc/head.cu: clear_head_backward; CLEAR_GEMM_GROUP changes it for diagnostics)
+    paired_bwd = need_dhidden and need_dweight and not dw_f32
     n_bwd = 0 if not write_grad else (1 if paired_bwd else int(need_dhidden) + int(need_dweight))
     launches += n_blocks * (2 + int(needs_ref and not paired_proj) + n_bwd) + 1 + int(bool(n_seqs))
     if compact_ignored:   # compact, gather labels (+ row weights), gather hidden, scatter loss terms (+ dH); a dH contraction on its
