@@ -134,6 +134,24 @@ __device__ __forceinline__ void merge_lse2(const float2* ps, const float2* pt, i
   lse_t = mb + logf(warp_sum(sb));
 }
 
+// One operand, one round trip to L2 (n <= 128 tiles: every lane fetches its up to four partials before any arithmetic).
+__device__ __forceinline__ float merge_lse1(const float2* ps, int n) {
+  if (n > 128) return merge_lse(ps, n);
+  const int lane = threadIdx.x & 31;
+  float2 a[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = lane + 32 * k;
+    a[k] = (i < n) ? ps[i] : make_float2(-INFINITY, 0.f);
+  }
+  const float ma = warp_max(fmaxf(fmaxf(a[0].x, a[1].x), fmaxf(a[2].x, a[3].x)));
+  float sa = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (lane + 32 * k < n) sa += a[k].y * exp2f((a[k].x - ma) * kLog2e);
+  return ma + logf(warp_sum(sa));
+}
+
 template <int kThreads>
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -380,8 +398,17 @@ __global__ void __launch_bounds__(kThreads) rowloss_twopass_kernel(const RowLoss
   const char* zr = kNeedsRef ? static_cast<const char*>(a.ref_logits) + row * a.ref_ld * (kRefF32 ? 4 : 2) : nullptr;
   RowConsts c;
   float lse_t = 0.f;
-  if constexpr (kNeedsRef) merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, c.lse_s, lse_t);
-  else c.lse_s = merge_lse(a.lse_part + row * a.n_vtiles, a.n_vtiles);
+  {  // warp 0 merges the student's partials, warp 1 the teacher's (see rowloss_npo1_kernel: these kernels are issue-bound too)
+    __shared__ float row_lse[2];
+    if (threadIdx.x < (kNeedsRef ? 64 : 32)) {
+      const int wq = threadIdx.x >> 5;
+      const float l = merge_lse1((wq ? a.ref_lse_part : a.lse_part) + row * a.n_vtiles, a.n_vtiles);
+      if ((threadIdx.x & 31) == 0) row_lse[wq] = l;
+    }
+    __syncthreads();
+    c.lse_s = row_lse[0];
+    if constexpr (kNeedsRef) lse_t = row_lse[1];
+  }
   c.nls2 = -c.lse_s * kLog2e;
   c.nlt2 = -lse_t * kLog2e;
   c.dlse = lse_t - c.lse_s;
@@ -492,7 +519,8 @@ __device__ __forceinline__ void npo8_eval(const float (&x)[8], const float (&r)[
     o.s[h + 2] = o.p[h + 2] * i2;
     o.s[h + 3] = o.p[h + 3] * i3;
     stat += (o.s[h] + o.s[h + 1]) + (o.s[h + 2] + o.s[h + 3]);
-    if (want_loss) lossl2 += ptx::lg2_approx(((A[h] * i0) * (A[h + 1] * i1)) * ((A[h + 2] * i2) * (A[h + 3] * i3)));
+    // prod_j A_j / B_j = (prod_j A_j) * inv: four multiplies instead of seven (A_j >= 1e-8: the product of four stays normal)
+    if (want_loss) lossl2 += ptx::lg2_approx(((A[h] * A[h + 1]) * (A[h + 2] * A[h + 3])) * inv);
   }
 }
 
@@ -519,12 +547,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) rowloss_npo1_kernel(cons
     nx = reinterpret_cast<const uint4*>(z)[threadIdx.x];
     nr = ld_ref8<kRefF32>(zr, threadIdx.x);
   }
-  float lse_s, lse_t;
-  merge_lse2(a.lse_part + row * a.n_vtiles, a.ref_lse_part + row * a.n_vtiles, a.n_vtiles, lse_s, lse_t);
+  // The row's two log-sum-exps: warp 0 merges the student's partials, warp 1 the teacher's, everybody else waits at the
+  // barrier with its first vectors in flight.  (Every warp used to merge both redundantly, "cheaper than a barrier" — but the
+  // kernel is bound by instruction issue (73 % of the issue slots, 3 eligible warps per scheduler and cycle: ncu, round 2), and
+  // the redundant merges were 17 % of all instructions executed.)
+  __shared__ float row_lse[2];
+  if (threadIdx.x < 64) {
+    const int wq = threadIdx.x >> 5;
+    const float l = merge_lse1((wq ? a.ref_lse_part : a.lse_part) + row * a.n_vtiles, a.n_vtiles);
+    if ((threadIdx.x & 31) == 0) row_lse[wq] = l;
+  }
+  __syncthreads();
+  const float lse_s = row_lse[0], lse_t = row_lse[1];
   const float nls2 = -lse_s * kLog2e, nlt2 = -lse_t * kLog2e;
   const float w = a.row_weight ? a.row_weight[row] : 1.f;
   const float g = a.grad_scale * (a.scale_dev ? *a.scale_dev : 1.f) * w;
   float stat = 0.f, lossl2 = 0.f;
+  // (Measured and rejected, round 2: the same loop with two register sets that swap roles and running pointers — 11 % fewer
+  // instructions, 5 % SLOWER: once the redundant merges were gone the kernel stopped being bound by instruction issue alone.)
   for (int v = threadIdx.x; v < nfull; v += kThreads) {
     const uint4 cx = nx;
     const RefVec<kRefF32> cr = nr;
