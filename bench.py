@@ -16,7 +16,7 @@ Prints ONE JSON line (rank 0).
 `value_with_stage_events`  the same K steps again, the LIBRARY recording CUDA events between its stages
            (ClearHeadArgs.stage_events: projection(s) / row pass / backward contractions): these feed `roofline`.  They stay
            out of the headline loop because an event between two launches keeps the next kernel from filling the SMs
-           the previous persistent grid's last tiles leave idle (+0.2 ms per 6.6 ms step).
+           the previous persistent grid's last tiles leave idle (0.1-0.5 ms per step on the boxes of this pool).
 `e2e`      the same step through the public API with HOST (pinned) inputs: every step copies the hidden states, the
            teacher's hidden states and the labels host->device and reads the loss back (copies double-buffered on a side
            stream; all of them inside the timed region).
@@ -597,7 +597,7 @@ def main():
 
     # ---- the same K steps again with the library recording CUDA events between its stages (the live roofline numbers) --
     # Kept out of the headline region: an event between two launches makes the next kernel wait for the previous persistent
-    # grid to drain completely instead of filling the SMs its last tiles leave idle (measured: +0.2 ms per 6.6 ms step).
+    # grid to drain completely instead of filling the SMs its last tiles leave idle (measured: 0.1-0.5 ms per step).
     with head.StageTimer() as warm:      # the event pool and the allocator in their steady state for this mode too
         for i in range(2):
             step(i, dev_in)
