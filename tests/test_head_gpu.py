@@ -634,6 +634,40 @@ def test_gemm_layouts_groups_and_tile_orders(cta_group, layout, raster):
     assert (D[:, n:] == 7.0).all(), "columns beyond N must not be written"
 
 
+@pytest.mark.parametrize("k", [64, 576, 2048])
+@pytest.mark.parametrize("layout", ["k_k", "mn_mn"])
+def test_gemm_scheduler_ring_wraps_many_times(k, layout):
+    """The claimed-work ring (8 slots of decoded items handed over by st.async, two TMA threads, fence-free hand-backs) under
+    boundary-dominated work: 2048 output tiles of 1 / 9 / 32 K blocks (about 27 items per CTA pair: the ring wraps three times,
+    items shorter and longer than the hand-on distance), five launches back to back on one stream (the work counters re-arm
+    themselves), every launch checked against cuBLAS in fp32."""
+    import ctypes as C
+
+    from multimodal_unlearning_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    m, n = 8192, 16384
+    g = torch.Generator(device=dev).manual_seed(100 + k)
+    A = torch.randn(m, k, generator=g, device=dev).to(torch.bfloat16)
+    B = torch.randn(n, k, generator=g, device=dev).to(torch.bfloat16)
+    major = 0 if layout == "k_k" else 1
+    a_st = A.contiguous() if major == 0 else A.t().contiguous()
+    b_st = B.contiguous() if major == 0 else B.t().contiguous()
+    want = A.float() @ B.float().t()
+    scale = want.abs().max().item()
+    outs = [torch.full((m, n), 3.0, dtype=torch.bfloat16, device=dev) for _ in range(5)]
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for D in outs:
+        args = _lib.GemmArgs(a=a_st.data_ptr(), b=b_st.data_ptr(), d=D.data_ptr(), lse_part=None, lda=a_st.stride(0),
+                             ldb=b_st.stride(0), ldd=D.stride(0), m=m, n=n, k=k, a_major=major, b_major=major, d_f32=0,
+                             accumulate=0, cta_group=0, raster_m_fast=-1, k_splits=1)
+        _lib.check(lib.clear_gemm_bf16(C.byref(args), stream), "clear_gemm_bf16")
+    torch.cuda.synchronize()
+    for D in outs:
+        assert (D.float() - want).abs().max().item() <= 2 ** -7 * scale
+        assert torch.equal(D, outs[0]), "every launch computes the same bits"
+
+
 @pytest.mark.parametrize("reduction", ["reference", "seq_mean", "sum"])
 @pytest.mark.parametrize("valid_frac", [0.05, 0.5, 1.0, 0.0])
 def test_ce_row_compaction_is_exact(reduction, valid_frac):
